@@ -1,0 +1,458 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores.
+//
+//   out[p, n] = sum_{tap, k} in[p + tap, k] * Wp[tap][n][k]          (zero padding)
+//
+// GEMM view: M = 128 output pixels per tile (a Wt x Ht x Bt box of the NHWC tensor), N = BLOCK_N
+// output channels, K = taps x (C0 + C1) input channels.  The input is the *virtual* concatenation of
+// two NHWC tensors (x_t and h_{t-1} of the ConvLSTM cell, reference train/unet.py:28; the skip and
+// the up-sampled tensor of an Up block, unet.py:98): each K block comes from one TMA box of one of
+// the two tensors, so no concatenated copy ever exists.  Zero padding is the TMA out-of-bounds
+// fill: the box of tap (ky,kx) starts at (w0+kx-pad, h0+ky-pad), possibly negative.
+//
+// Warp roles (256 threads, one CTA per SM, persistent over tiles):
+//   warp 0   TMA producer           : A box + B box per K block into a STAGES-deep smem ring
+//   warp 1   MMA issuer (1 thread)  : tcgen05.mma kind::f16, fp32 accumulators in TMEM (2 stages)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue              : tcgen05.ld -> bias / gate math -> global stores
+//
+// Epilogues:
+//   EPI_STORE  bias, optional ReLU, bf16 or fp32 output, optionally split over two destination
+//              tensors (dgrad of the virtual concat: [dx ; dh]).
+//   EPI_LSTM   the N tile holds the four gates of CHT hidden channels (weights are packed
+//              gate-interleaved), so i,f,g,o of a (pixel, channel) sit in one thread's TMEM lane:
+//              sigma,sigma,tanh,sigma, c' = f*c + i*g, h' = o*tanh(c')  (unet.py:29-35) are applied
+//              in registers and only h' (bf16), c' (fp32) and the activated gates (bf16, for BPTT)
+//              are written; the 4*Ch pre-activations never reach HBM.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int NUM_THREADS = 256;
+static constexpr int EPI_WARP0 = 4;
+
+template <int BLOCK_N>
+struct TcCfg {
+    static constexpr int A_BYTES = BLOCK_M * 128;  // at kc = 64 (bf16)
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct TileCoord {
+    int n0, t, b0, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile, int block_n) {
+    TileCoord tc;
+    int nt = tile / p.num_m_tiles;
+    int m = tile - nt * p.num_m_tiles;
+    tc.n0 = nt * block_n;
+    int wt = m % p.tiles_w;
+    m /= p.tiles_w;
+    int ht = m % p.tiles_h;
+    m /= p.tiles_h;
+    int bt = m % p.tiles_b;
+    tc.t = m / p.tiles_b;
+    tc.w0 = wt * p.Wt;
+    tc.h0 = ht * p.Ht;
+    tc.b0 = bt * p.Bt;
+    return tc;
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+               const __grid_constant__ CUtensorMap tm_b, const ConvTcParams p) {
+    using Cfg = TcCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_ptr_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int taps = p.ksize * p.ksize;
+    const int chunks0 = p.C0 / p.kc;
+    const int chunks1 = p.C1 / p.kc;
+    const int chunks = chunks0 + chunks1;
+    const int num_kb = taps * chunks;
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const uint32_t a_bytes = BLOCK_M * p.kc * 2;
+    const uint32_t b_bytes = BLOCK_N * p.kc * 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a0);
+        if (p.C1 > 0) prefetch_tmap(&tm_a1);
+        prefetch_tmap(&tm_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // =================================== TMA producer ===================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile, BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / chunks;
+                    const int rem = kb - tap * chunks;
+                    const int ky = tap / p.ksize;
+                    const int kx = tap - ky * p.ksize;
+                    mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
+                    mbar_arrive_expect_tx(full_bar(stage), a_bytes + b_bytes);
+                    const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+                    if (rem < chunks0) {
+                        tma_load_5d(a_dst, &tm_a0, full_bar(stage), rem * p.kc, tc.w0 + kx - p.pad,
+                                    tc.h0 + ky - p.pad, tc.b0, tc.t);
+                    } else {
+                        tma_load_5d(a_dst, &tm_a1, full_bar(stage), (rem - chunks0) * p.kc,
+                                    tc.w0 + kx - p.pad, tc.h0 + ky - p.pad, tc.b0, tc.t);
+                    }
+                    tma_load_3d(b_dst, &tm_b, full_bar(stage), rem * p.kc, tc.n0, tap);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =================================== MMA issuer =====================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            // K-major swizzled operand tiles: rows of kc*2 bytes, 8-row atoms => SBO = 8 * row bytes
+            const uint32_t row_bytes = p.kc * 2;
+            const uint32_t layout_type = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
+            const uint32_t sbo = 8u * row_bytes;
+            const int mma_per_kb = p.kc / 16;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                    const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, layout_type);
+                    const uint64_t bdesc = make_smem_desc(b_addr, 16, sbo, layout_type);
+#pragma unroll 4
+                    for (int k = 0; k < mma_per_kb; ++k) {
+                        // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in >>4 units
+                        umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // =================================== epilogue =======================================
+        const int q = warp - EPI_WARP0;  // TMEM lane quarter == warp % 4
+        const int r = q * 32 + lane;     // row of the M tile
+        const int wi = r % p.Wt;
+        const int hi = (r / p.Wt) % p.Ht;
+        const int bi = r / (p.Wt * p.Ht);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile, BLOCK_N);
+            const bool valid = (tc.h0 + hi < p.H) && (tc.b0 + bi < p.B);
+            const long long pix =
+                ((static_cast<long long>(tc.t) * p.B + tc.b0 + bi) * p.H + tc.h0 + hi) * p.W + tc.w0 + wi;
+            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 400 + acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
+
+            if constexpr (EPI == EPI_STORE) {
+#pragma unroll 1
+                for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
+                    const int ncol = tc.n0 + c16 * 16;
+                    if (ncol >= p.N) break;  // warp-uniform
+                    uint32_t v[16];
+                    tmem_ld16(t_row + c16 * 16, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ncol + j);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        const bool second = ncol >= p.split;
+                        const long long off = second ? pix * p.ld1 + (ncol - p.split) : pix * p.ld0 + ncol;
+                        void* base = second ? p.dst1 : p.dst0;
+                        if (p.out_fp32) {
+                            float4* o = reinterpret_cast<float4*>(static_cast<float*>(base) + off);
+                            if (p.accumulate) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float4 old = o[j];
+                                    o[j] = make_float4(old.x + f[4 * j], old.y + f[4 * j + 1],
+                                                       old.z + f[4 * j + 2], old.w + f[4 * j + 3]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            }
+                        } else {
+                            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off);
+                            o[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                            o[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                              pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                        }
+                    }
+                }
+            } else {
+                // ---- fused LSTM cell update (reference train/unet.py:29-35) ----
+                constexpr int CHT = BLOCK_N / 4;
+                const int Ch = p.N >> 2;
+                const int ch0 = (tc.n0 >> 2);  // first hidden channel of this N tile
+#pragma unroll 1
+                for (int j0 = 0; j0 < CHT; j0 += 16) {
+                    uint32_t vi[16], vf[16], vg[16], vo[16];
+                    tmem_ld16(t_row + 0 * CHT + j0, vi);
+                    tmem_ld16(t_row + 1 * CHT + j0, vf);
+                    tmem_ld16(t_row + 2 * CHT + j0, vg);
+                    tmem_ld16(t_row + 3 * CHT + j0, vo);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int ch = ch0 + j0;
+                        const long long coff = pix * Ch + ch;
+                        float cp[16];
+                        if (p.c_prev) {
+                            const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + coff);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 t4 = c4[j];
+                                cp[4 * j] = t4.x;
+                                cp[4 * j + 1] = t4.y;
+                                cp[4 * j + 2] = t4.z;
+                                cp[4 * j + 3] = t4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+                        }
+                        float gi[16], gf[16], gg[16], go[16], cn[16], hn[16];
+                        const float* bp = p.bias ? p.bias + tc.n0 + j0 : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float zi = __uint_as_float(vi[j]);
+                            float zf = __uint_as_float(vf[j]);
+                            float zg = __uint_as_float(vg[j]);
+                            float zo = __uint_as_float(vo[j]);
+                            if (bp) {
+                                zi += __ldg(bp + j);
+                                zf += __ldg(bp + CHT + j);
+                                zg += __ldg(bp + 2 * CHT + j);
+                                zo += __ldg(bp + 3 * CHT + j);
+                            }
+                            gi[j] = fast_sigmoid(zi);
+                            gf[j] = fast_sigmoid(zf);
+                            gg[j] = fast_tanh(zg);
+                            go[j] = fast_sigmoid(zo);
+                            cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
+                            hn[j] = go[j] * fast_tanh(cn[j]);
+                        }
+                        float4* co = reinterpret_cast<float4*>(p.c_next + coff);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            co[j] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+                        uint4* ho = reinterpret_cast<uint4*>(p.h_next + coff);
+                        ho[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                           pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+                        ho[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]),
+                                           pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
+                        if (p.gates_out) {
+                            __nv_bfloat16* gb = p.gates_out + pix * (4LL * Ch) + ch;
+                            auto st16 = [](__nv_bfloat16* dst, const float* s) {
+                                uint4* o = reinterpret_cast<uint4*>(dst);
+                                o[0] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]),
+                                                  pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+                                o[1] = make_uint4(pack_bf16x2(s[8], s[9]), pack_bf16x2(s[10], s[11]),
+                                                  pack_bf16x2(s[12], s[13]), pack_bf16x2(s[14], s[15]));
+                            };
+                            st16(gb, gi);
+                            st16(gb + Ch, gf);
+                            st16(gb + 2 * Ch, gg);
+                            st16(gb + 3 * Ch, go);
+                        }
+                    }
+                }
+            }
+            // release the accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+int pick_block_n(int N, int epi) {
+    if (epi == EPI_LSTM) {
+        int Ch = N / 4;
+        if (Ch % 64 == 0) return 256;
+        if (Ch % 32 == 0) return 128;
+        if (Ch % 16 == 0) return 64;
+        return 0;
+    }
+    if (N % 16 != 0) return 0;
+    if (N >= 256 || N > 128) return 256;
+    if (N > 64) return 128;
+    return 64;
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb,
+                       const ConvTcParams& p, cudaStream_t stream) {
+    using Cfg = TcCfg<BLOCK_N>;
+    auto kern = conv_tc_kernel<BLOCK_N, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int total = p.num_m_tiles * p.num_n_tiles;
+    int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta0, ta1, tb, p);
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi,
+                   cudaStream_t stream) {
+    if (p.C1 > 0 && !src1) {
+        set_last_error("conv_tc: C1 > 0 but src1 is null");
+        return B200_ERR_ARG;
+    }
+    const int Ct = p.wK > 0 ? p.wK : p.C0 + p.C1;
+    int kc = 64;
+    while (kc >= 16 && ((p.C0 % kc) != 0 || (p.C1 % kc) != 0)) kc >>= 1;
+    if (kc < 16 || p.C0 <= 0) {
+        set_last_error("conv_tc: channel counts C0=%d C1=%d are not multiples of 16", p.C0, p.C1);
+        return B200_ERR_SHAPE;
+    }
+    p.kc = kc;
+    const int block_n = pick_block_n(p.N, epi);
+    if (block_n == 0) {
+        set_last_error("conv_tc: N=%d not supported for epilogue %d", p.N, epi);
+        return B200_ERR_SHAPE;
+    }
+    MTile mt;
+    if (!plan_mtile(p.B, p.H, p.W, BLOCK_M, &mt)) {
+        set_last_error("conv_tc: spatial shape B=%d H=%d W=%d cannot be tiled", p.B, p.H, p.W);
+        return B200_ERR_SHAPE;
+    }
+    p.Wt = mt.Wt;
+    p.Ht = mt.Ht;
+    p.Bt = mt.Bt;
+    p.tiles_w = mt.tiles_w;
+    p.tiles_h = mt.tiles_h;
+    p.tiles_b = mt.tiles_b;
+    p.num_m_tiles = p.T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
+    p.num_n_tiles = (p.N + block_n - 1) / block_n;
+    p.pad = p.ksize / 2;
+    p.err_flag = device_error_flag();
+
+    CUtensorMap ta0, ta1, tb;
+    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, p.T, kc, mt.Wt, mt.Ht, mt.Bt);
+    if (rc != B200_OK) return rc;
+    if (p.C1 > 0) {
+        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, p.T, kc, mt.Wt, mt.Ht, mt.Bt);
+        if (rc != B200_OK) return rc;
+    } else {
+        ta1 = ta0;
+    }
+    // rows beyond N inside the last N tile are TMA out-of-bounds reads => zero filled
+    rc = make_w_tmap(&tb, wpacked, Ct, p.N, p.ksize * p.ksize, kc, block_n);
+    if (rc != B200_OK) return rc;
+
+    if (epi == EPI_LSTM) {
+        switch (block_n) {
+            case 256: return launch_impl<256, EPI_LSTM>(ta0, ta1, tb, p, stream);
+            case 128: return launch_impl<128, EPI_LSTM>(ta0, ta1, tb, p, stream);
+            default: return launch_impl<64, EPI_LSTM>(ta0, ta1, tb, p, stream);
+        }
+    }
+    switch (block_n) {
+        case 256: return launch_impl<256, EPI_STORE>(ta0, ta1, tb, p, stream);
+        case 128: return launch_impl<128, EPI_STORE>(ta0, ta1, tb, p, stream);
+        default: return launch_impl<64, EPI_STORE>(ta0, ta1, tb, p, stream);
+    }
+}
+
+}  // namespace b200

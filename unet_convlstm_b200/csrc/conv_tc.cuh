@@ -1,0 +1,48 @@
+// Parameters of the tcgen05 implicit-GEMM convolution (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum ConvEpilogue : int {
+    EPI_STORE = 0,  // out = acc (+bias) (+relu) -> bf16 / fp32, optionally split over two tensors
+    EPI_LSTM = 1,   // gate-interleaved N tile: sigma/tanh gate math + c/h update (unet.py:29-35)
+};
+
+struct ConvTcParams {
+    // problem
+    int T, B, H, W;   // T groups of B images of H x W pixels (NHWC)
+    int C0, C1;       // channels of source 0 / source 1 (C1 == 0: single source)
+    int N;            // GEMM N (output channels; 4*Ch for the LSTM epilogue)
+    int ksize, pad;   // square filter size (odd) and padding
+    int kc;           // channels per K block (64 / 32 / 16)
+    int wK;           // row length of the packed weights (0: C0 + C1)
+    // M tiling
+    int Wt, Ht, Bt;
+    int tiles_w, tiles_h, tiles_b;
+    int num_m_tiles, num_n_tiles;
+    // EPI_STORE
+    void* dst0;
+    void* dst1;
+    long long ld0, ld1;  // row strides (elements)
+    int split;           // columns [0,split) -> dst0, [split,N) -> dst1
+    int out_fp32;        // 0: bf16, 1: fp32
+    int relu;
+    int accumulate;      // fp32 only: dst += value
+    const float* bias;   // [N] (packed order) or nullptr
+    // EPI_LSTM  (Ch = N/4; packed column = (n_tile*4 + gate)*CHT + j)
+    const float* c_prev;        // [P, Ch] fp32 or nullptr (zeros)
+    float* c_next;              // [P, Ch] fp32
+    __nv_bfloat16* h_next;      // [P, Ch] bf16
+    __nv_bfloat16* gates_out;   // [P, 4, Ch] bf16 post-activation i,f,g,o or nullptr
+    int* err_flag;
+};
+
+// Launches the kernel for one problem.  All pointers are device pointers; maps are built per call.
+int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi,
+                   cudaStream_t stream);
+
+// Picks BLOCK_N for a given GEMM N (multiple of 16).  LSTM epilogue needs N % 64 == 0.
+int pick_block_n(int N, int epi);
+
+}  // namespace b200
