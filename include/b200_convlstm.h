@@ -49,6 +49,14 @@ int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch
                               const void* wpacked, const float* bias_packed, const float* c_prev,
                               float* c_next, void* h_next, void* gates_out, int ksize, void* stream);
 
+/* Weight gradient of a convolution, summed over all T*B images (autograd of nn.Conv2d, unet.py:19
+ * and :70-71; for the ConvLSTM this is the BPTT sum over timesteps):
+ *   dw[tap][n][koff + k] += sum_{t,p} dz[t,p,n] * src[t, p+tap, k]
+ * dz: bf16 [T][B][H][W][Nz], src: bf16 [T][B][H][W][Csrc], dw: fp32 [k*k][Nz][ldk], zero-initialised
+ * by the caller (partial sums are combined with fp32 reductions). */
+int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
+                  int ksize, float* dw, long long ldk, int koff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,152 @@
+"""The numpy oracle (oracle/unet_oracle.py) against fixtures produced by the reference itself
+(tests/golden/make_golden.py): forward, hand-derived backward, BatchNorm buffers, state carry."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import unet_oracle as O
+
+TOL = 2e-6  # fixtures store gradients as fp32; everything is computed in fp64
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    p = {k[2:]: z[k].astype(np.float64) if z[k].dtype != np.int64 else z[k] for k in z.files if k.startswith("p.")}
+    return z, p
+
+
+@pytest.mark.parametrize("name", ["convlstm_c8_l1_zero.npz", "convlstm_c6_12_l2_state.npz", "convlstm_c16_l1_state.npz"])
+def test_convlstm_matches_reference(golden_dir, name):
+    z, p = load(golden_dir, name)
+    cin, ch, L, B, T, H, W, with_state = z["meta"]
+    layers = [(p[f"layers.{l}.conv.weight"], p[f"layers.{l}.conv.bias"]) for l in range(L)]
+    state = [(z[f"h0{l}"], z[f"c0{l}"]) for l in range(L)] if with_state else None
+    out, new_state, caches = O.convlstm_fwd(list(z["x"]), layers, state)
+    assert rel(np.stack(out), z["out"]) < 1e-10
+    for l in range(L):
+        assert rel(new_state[l][0], z[f"hT{l}"]) < 1e-10
+        assert rel(new_state[l][1], z[f"cT{l}"]) < 1e-10
+    dstate = [None] * (L - 1) + [(z["dh_last"], z["dc_last"])]
+    dx, wg, d0 = O.convlstm_bwd(caches, list(z["dout"]), dstate)
+    assert rel(np.stack(dx), z["dx"]) < 1e-10
+    for l in range(L):
+        assert rel(wg[l][0], z[f"g.layers.{l}.conv.weight"]) < TOL
+        assert rel(wg[l][1], z[f"g.layers.{l}.conv.bias"]) < TOL
+        if with_state:
+            assert rel(d0[l][0], z[f"dh0{l}"]) < 1e-10
+            assert rel(d0[l][1], z[f"dc0{l}"]) < 1e-10
+
+
+@pytest.mark.parametrize("name,kind", [("double_3_8.npz", "double"), ("down_8_16.npz", "down"),
+                                       ("up_16_8.npz", "up"), ("up_16_8_pad.npz", "up")])
+def test_blocks_match_reference(golden_dir, name, kind):
+    z, p = load(golden_dir, name)
+    tp = O.Tape(p, training=True)
+    if kind == "double":
+        y, c = O.double_conv_fwd(tp, "net", z["x0"])
+        dxs = (O.double_conv_bwd(tp, "net", c, z["dy"]),)
+    elif kind == "down":
+        y, c = O.down_fwd(tp, "", z["x0"]) if False else O.down_fwd(_Prefixed(tp), "X", z["x0"])
+        dxs = (O.down_bwd(_Prefixed(tp), "X", c, z["dy"]),)
+    else:
+        y, c = O.up_fwd(_Prefixed(tp), "X", z["x0"], z["x1"])
+        dxs = O.up_bwd(_Prefixed(tp), "X", c, z["dy"])
+    assert rel(y, z["y_train"]) < 1e-10
+    for i, dx in enumerate(dxs):
+        assert rel(dx, z[f"dx{i}"]) < 1e-9
+    for k in z.files:
+        if k.startswith("g."):
+            g = tp.grads[k[2:]]
+            ref = z[k]
+            # conv biases feeding a BatchNorm have an exactly-zero true gradient: compare absolutely
+            if np.abs(ref).max() < 1e-9:
+                assert np.abs(g).max() < 1e-9
+            else:
+                assert rel(g, ref) < TOL, k
+        if k.startswith("after."):
+            assert rel(np.asarray(tp.buf(k[6:]), dtype=np.float64), z[k].astype(np.float64)) < 1e-12, k
+    tpe = O.Tape({**p, **{k: v for k, v in tp.new_buffers.items()}}, training=False)
+    if kind == "double":
+        ye, _ = O.double_conv_fwd(tpe, "net", z["x0"])
+    elif kind == "down":
+        ye, _ = O.down_fwd(_Prefixed(tpe), "X", z["x0"])
+    else:
+        ye, _ = O.up_fwd(_Prefixed(tpe), "X", z["x0"], z["x1"])
+    assert rel(ye, z["y_eval"]) < 1e-10
+
+
+class _Prefixed:
+    """Lets the block-level oracle functions (which expect `<pre>.` keys) run on a bare block's
+    state_dict: strips the dummy prefix 'X.'."""
+
+    def __init__(self, tp):
+        self._tp = tp
+        self.training = tp.training
+        self.p = _StripDict(tp.p)
+        self.new_buffers = _StripDict(tp.new_buffers)
+        self.grads = tp.grads
+
+    def buf(self, name):
+        return self._tp.buf(name[2:])
+
+    def add(self, name, g):
+        self._tp.add(name[2:], g)
+
+
+class _StripDict:
+    def __init__(self, d):
+        self.d = d
+
+    def __getitem__(self, k):
+        return self.d[k[2:]]
+
+    def __setitem__(self, k, v):
+        self.d[k[2:]] = v
+
+    def __contains__(self, k):
+        return k[2:] in self.d
+
+    def get(self, k, default=None):
+        return self.d.get(k[2:], default)
+
+
+@pytest.mark.parametrize("name", ["model_b4_skip.npz", "model_b2_noskip_l2.npz"])
+def test_model_matches_reference(golden_dir, name):
+    z, p = load(golden_dir, name)
+    base_ch, skip, L, B, T, H, W = z["meta"]
+    y, st, tp, caches = O.temporal_unet_fwd(p, z["x"], training=True)
+    assert rel(y, z["y_train"]) < 1e-9
+    for l in range(L):
+        assert rel(st[l][0], z[f"hT{l}"]) < 1e-9
+        assert rel(st[l][1], z[f"cT{l}"]) < 1e-9
+    dx = O.temporal_unet_bwd(tp, caches, z["dy"])
+    assert rel(dx, z["dx"]) < 1e-7
+    for k in z.files:
+        if k.startswith("g."):
+            ref = z[k].astype(np.float64)
+            g = tp.grads[k[2:]]
+            if np.abs(ref).max() < 1e-7 * max(1.0, np.abs(z["dy"]).max()):
+                assert np.abs(g).max() < 1e-6, k
+            else:
+                assert rel(g, ref) < 5e-6, k
+        if k.startswith("after."):
+            assert rel(np.asarray(tp.buf(k[6:]), dtype=np.float64), z[k].astype(np.float64)) < 1e-10, k
+    # eval mode with the updated running statistics, and the state round trip (unet.py:185)
+    p_eval = {**p, **tp.new_buffers}
+    ye, _, _, _ = O.temporal_unet_fwd(p_eval, z["x"], training=False)
+    assert rel(ye, z["y_eval"]) < 1e-9
+    k = T // 2
+    y1, s1, _, _ = O.temporal_unet_fwd(p_eval, z["x"][:, :k], training=False)
+    y2, _, _, _ = O.temporal_unet_fwd(p_eval, z["x"][:, k:], state=s1, training=False)
+    assert rel(np.concatenate([y1, y2], axis=1), z["y_eval_split"]) < 1e-9
+    assert int(tp.buf("inc.net.1.num_batches_tracked")) == T
+
+
+def test_fixture_set_is_complete(golden_dir):
+    assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 9

@@ -117,6 +117,51 @@ def test_lstm(B, H, W, Cin, Ch, with_state=True):
     return ok
 
 
+lib.b200_wgrad_tc.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, ci, vp, ll, ci, vp]
+
+
+def test_wgrad(T, B, H, W, Nz, C0, C1, k=3):
+    g = torch.Generator(device=dev).manual_seed(3)
+    dz = torch.randn(T, B, H, W, Nz, device=dev, generator=g).to(torch.bfloat16)
+    s0 = torch.randn(T, B, H, W, C0, device=dev, generator=g).to(torch.bfloat16)
+    s1 = torch.randn(T, B, H, W, C1, device=dev, generator=g).to(torch.bfloat16) if C1 else None
+    Ct = C0 + C1
+    dw = torch.zeros(k * k, Nz, Ct, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.b200_wgrad_tc(ptr(dz), Nz, ptr(s0), C0, T, B, H, W, k, ptr(dw), Ct, 0, st), "wgrad0")
+    if s1 is not None:
+        check(lib.b200_wgrad_tc(ptr(dz), Nz, ptr(s1), C1, T, B, H, W, k, ptr(dw), Ct, C0, st), "wgrad1")
+    torch.cuda.synchronize()
+    xin = s0 if s1 is None else torch.cat([s0, s1], dim=-1)
+    xin = xin.float().reshape(T * B, H, W, Ct).permute(0, 3, 1, 2).contiguous()
+    dzz = dz.float().reshape(T * B, H, W, Nz).permute(0, 3, 1, 2).contiguous()
+    ref = torch.nn.grad.conv2d_weight(xin, (Nz, Ct, k, k), dzz, padding=k // 2)  # OIHW
+    ref = ref.permute(2, 3, 0, 1).reshape(k * k, Nz, Ct)
+    e = relerr(dw, ref)
+    ok = e < 1e-4
+    print(f"wgrad T={T} B={B} H={H} W={W} Nz={Nz} C0={C0} C1={C1} k={k}: relerr={e:.3e} {'OK' if ok else 'FAIL'}",
+          flush=True)
+    return ok
+
+
+def bench_wgrad(T, B, H, W, Nz, C, iters=5):
+    dz = torch.randn(T, B, H, W, Nz, device=dev).to(torch.bfloat16)
+    s0 = torch.randn(T, B, H, W, C, device=dev).to(torch.bfloat16)
+    dw = torch.zeros(9, Nz, C, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        lib.b200_wgrad_tc(ptr(dz), Nz, ptr(s0), C, T, B, H, W, 3, ptr(dw), C, 0, st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        lib.b200_wgrad_tc(ptr(dz), Nz, ptr(s0), C, T, B, H, W, 3, ptr(dw), C, 0, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 2.0 * T * B * H * W * 9 * C * Nz
+    print(f"bench wgrad T={T} B={B} H={H} W={W} Nz={Nz} C={C}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def bench_lstm(B, H, W, C, iters=20):
     x = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
     h = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
@@ -158,7 +203,17 @@ if __name__ == "__main__":
     ok &= test_lstm(4, 8, 8, 128, 128)
     ok &= test_lstm(2, 32, 32, 32, 32)
     ok &= test_lstm(2, 16, 16, 32, 16)
+    ok &= test_wgrad(1, 2, 8, 8, 128, 64, 0)
+    ok &= test_wgrad(2, 4, 4, 4, 256, 128, 128)
+    ok &= test_wgrad(3, 2, 16, 16, 64, 64, 0)
+    ok &= test_wgrad(2, 2, 32, 32, 128, 32, 96)
+    ok &= test_wgrad(1, 1, 12, 16, 64, 16, 0)
+    ok &= test_wgrad(2, 2, 8, 128, 320, 320, 0, k=1)
+    ok &= test_wgrad(4, 8, 64, 64, 64, 64, 0)
     print("ALL OK" if ok else "SOME FAILED", flush=True)
+    bench_wgrad(20, 256, 4, 4, 4096, 1024)
+    bench_wgrad(20, 256, 16, 16, 1024, 256)
+    bench_wgrad(4, 256, 64, 64, 64, 64)
     if ok:
         bench_lstm(256, 4, 4, 1024)
         bench_lstm(256, 8, 8, 512)

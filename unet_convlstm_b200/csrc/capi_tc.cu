@@ -5,6 +5,11 @@
 
 using namespace b200;
 
+namespace b200 {
+int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
+                    int ksize, float* dw, long long ldk, int koff, cudaStream_t stream);
+}
+
 extern "C" int b200_device_error(void) {
     int* f = device_error_flag();
     if (!f) return 0;
@@ -68,4 +73,14 @@ extern "C" int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_p
     // With h_prev == NULL (zero initial state, unet.py:23-25) the h half of K is skipped; the
     // packed weight rows still span Cin+Ch columns, so the weight map must keep the full K.
     return launch_conv_tc(x, h_prev, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
+                             int ksize, float* dw, long long ldk, int koff, void* stream) {
+    if (!dz || !src || !dw || Nz <= 0 || Csrc <= 0 || (ksize & 1) == 0 || koff < 0 || koff + Csrc > ldk) {
+        set_last_error("b200_wgrad_tc: bad arguments");
+        return B200_ERR_ARG;
+    }
+    return launch_wgrad_tc(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff,
+                           static_cast<cudaStream_t>(stream));
 }
