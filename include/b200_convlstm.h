@@ -57,6 +57,79 @@ int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch
 int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
                   int ksize, float* dw, long long ldk, int koff, void* stream);
 
+/* 1 if b200_wgrad_tc can tile this problem. */
+int b200_wgrad_tc_supported(int B, int H, int W, int Nz, int Csrc);
+
+/* ---- generic CUDA-core convolutions: the fp32 check mode (dtype_fp32 = 1, 1e-5 parity with the
+ * reference's fp32 arithmetic) and shapes the tcgen05 path cannot tile (dtype_fp32 = 0: bf16 storage).
+ * Same math and packed-weight layout as the *_tc entry points; IMG = T*B images. ---- */
+int b200_conv_simt_fwd(const void* src0, int C0, const void* src1, int C1, int IMG, int H, int W,
+                       const void* w, const float* bias, int N, int ksize, void* dst0, long long ld0,
+                       int split, void* dst1, long long ld1, int dtype_fp32, int out_fp32, int relu,
+                       void* stream);
+int b200_wgrad_simt(const void* dz, int Nz, const void* src, int Csrc, int IMG, int H, int W, int ksize,
+                    float* dw, long long ldk, int koff, int dtype_fp32, void* stream);
+
+/* ---- BatchNorm2d + ReLU of DoubleConv (unet.py:70-71), statistics per (t, channel) over the P = B*H*W
+ * pixels of one timestep because the reference calls the block once per timestep (unet.py:179-182,
+ * :196-202).  x, y, dy, dx: [T][P][C]; sum / sumsq / sum_g / sum_gx: double [T][C] workspaces. ---- */
+int b200_bn_stats(const void* x, int T, long long P, int C, int dtype_fp32, double* sum, double* sumsq,
+                  void* stream);
+/* training: mean/rstd/scale/shift [T][C] from the sums and T sequential momentum updates of the running
+ * estimates (unbiased variance); eval: scale/shift [1][C] from the running estimates. */
+int b200_bn_finalize(const double* sum, const double* sumsq, int T, long long n, int C, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                     int training, float* mean, float* rstd, float* scale, float* shift, void* stream);
+/* y = relu(x*scale[t][c] + shift[t][c]); tstride = C (training) or 0 (eval) */
+int b200_bn_relu_apply(const void* x, const float* scale, const float* shift, void* y, int T, long long P, int C,
+                       int tstride, int relu, int dtype_fp32, void* stream);
+/* autograd of BatchNorm2d+ReLU: g = dy*[y>0]; sum_g = sum g, sum_gx = sum g*xhat */
+int b200_bn_relu_bwd_reduce(const void* x, const void* dy, const float* mean, const float* rstd,
+                            const float* scale, const float* shift, int T, long long P, int C, int tstride,
+                            int dtype_fp32, double* sum_g, double* sum_gx, void* stream);
+int b200_bn_bwd_finalize(const double* sum_g, const double* sum_gx, int T, long long n, int C, int training,
+                         float* coef1, float* coef2, float* dgamma, float* dbeta, int accumulate, void* stream);
+/* dx = scale*(g - coef1 - xhat*coef2) */
+int b200_bn_relu_bwd_apply(const void* x, const void* dy, const float* mean, const float* rstd,
+                           const float* scale, const float* shift, const float* coef1, const float* coef2,
+                           void* dx, int T, long long P, int C, int tstride, int dtype_fp32, void* stream);
+
+/* nn.MaxPool2d(2) of Down (unet.py:81) and its backward (first maximum in scan order gets the gradient). */
+int b200_maxpool2_fwd(const void* x, void* y, long long IMG, int H, int W, int C, int dtype_fp32, void* stream);
+int b200_maxpool2_bwd(const void* x, const void* dy, void* dx, long long IMG, int H, int W, int C,
+                      int accumulate, int dtype_fp32, void* stream);
+
+/* ConvLSTM gate math when it is not fused into the GEMM epilogue (unet.py:29-35).  z: fp32 [P][4*Ch]
+ * pre-activations in the reference's chunk order i|f|g|o; gates: [P][4][Ch] activated. */
+int b200_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next,
+                        long long P, int Ch, int dtype_fp32, void* stream);
+/* One BPTT step of the gate math (autograd of unet.py:30-35): dh = dh_a + dh_b (either may be NULL),
+ * dc_next may be NULL; writes dz [P][4*Ch] (i|f|g|o) and dc_prev. */
+int b200_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_next, const void* dh_a,
+                        const void* dh_b, const float* dc_next, void* dz, float* dc_prev, long long P, int Ch,
+                        int dtype_fp32, void* stream);
+
+/* out[c] (+)= sum_rows x[row][c]  (bias gradients); workspace: double [C] */
+int b200_colsum(const void* x, long long rows, int C, int dtype_fp32, double* workspace, float* out,
+                int accumulate, void* stream);
+
+/* OutConv (1x1 conv, unet.py:101-107): y fp32 [P][O]; backward: dx (may be NULL), dw [O][C], db [O];
+ * workspace: double [max(C,O)] */
+int b200_outconv_fwd(const void* x, const float* w, const float* b, float* y, long long P, int C, int O,
+                     int dtype_fp32, void* stream);
+int b200_outconv_bwd(const void* x, const float* w, const float* dy, long long P, int C, int O, int dtype_fp32,
+                     void* dx, double* workspace, float* dw, float* db, int accumulate, void* stream);
+
+/* Pixel shuffle of ConvTranspose2d(k=2, stride=2) (unet.py:90) with the F.pad offsets of unet.py:95-97:
+ * z [IMG][H][W][4][C] (+bias) <-> y [IMG][Hd][Wd][C] at (2h+i+oy, 2w+j+ox), tap = 2i+j. */
+int b200_shuffle2x2(const void* src, void* dst, const float* bias, long long IMG, int H, int W, int C, int Hd,
+                    int Wd, int oy, int ox, int unshuffle, int dtype_fp32, void* stream);
+
+/* dst[i . dst_strides] (+)= src[i . src_strides] over a 5-D index space (layout changes at the module
+ * boundary: NCHW <-> NHWC; weight packing OIHW <-> [tap][N][K]).  Strides in elements. */
+int b200_strided_copy(const void* src, int src_fp32, void* dst, int dst_fp32, const long long* dims,
+                      const long long* src_strides, const long long* dst_strides, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

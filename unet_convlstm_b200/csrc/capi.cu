@@ -1,0 +1,280 @@
+// C-ABI entry points (declared in include/b200_convlstm.h): argument checks + kernel launches.
+// Nothing here allocates device memory; no exception crosses the boundary.
+#include "../../include/b200_convlstm.h"
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "pointwise.cuh"
+
+using namespace b200;
+
+namespace b200 {
+int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
+                    int ksize, float* dw, long long ldk, int koff, cudaStream_t stream);
+}
+
+extern "C" int b200_device_error(void) {
+    int* f = device_error_flag();
+    if (!f) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return B200_ERR_CUDA;
+    if (v != 0) cudaMemset(f, 0, sizeof(int));
+    return v;
+}
+
+extern "C" int b200_conv_tc_supported(int B, int H, int W, int C0, int C1, int N, int lstm) {
+    MTile mt;
+    if (!plan_mtile(B, H, W, 128, &mt)) return 0;
+    if (C0 <= 0 || C0 % 16 != 0 || C1 % 16 != 0) return 0;
+    if (pick_block_n(N, lstm ? EPI_LSTM : EPI_STORE) == 0) return 0;
+    return 1;
+}
+
+extern "C" int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
+                                int W, const void* wpacked, const float* bias, int N, int ksize,
+                                void* dst0, long long ld0, int split, void* dst1, long long ld1,
+                                int out_fp32, int relu, int accumulate, void* stream) {
+    if (!src0 || !wpacked || !dst0 || T <= 0 || N <= 0 || (ksize & 1) == 0) {
+        set_last_error("b200_conv_tc_fwd: bad arguments");
+        return B200_ERR_ARG;
+    }
+    if (split < 0 || split > N || (split < N && !dst1) || split % 16 != 0 || ld0 % 8 != 0 ||
+        (split < N && ld1 % 8 != 0)) {
+        set_last_error("b200_conv_tc_fwd: bad split/ld (split=%d N=%d ld0=%lld ld1=%lld)", split, N, ld0,
+                       ld1);
+        return B200_ERR_ARG;
+    }
+    if (accumulate && !out_fp32) {
+        set_last_error("b200_conv_tc_fwd: accumulate requires fp32 output");
+        return B200_ERR_ARG;
+    }
+    ConvTcParams p = {};
+    p.T = T; p.B = B; p.H = H; p.W = W;
+    p.C0 = C0; p.C1 = C1; p.N = N; p.ksize = ksize;
+    p.dst0 = dst0; p.dst1 = dst1; p.ld0 = ld0; p.ld1 = ld1; p.split = split;
+    p.out_fp32 = out_fp32; p.relu = relu; p.accumulate = accumulate; p.bias = bias;
+    return launch_conv_tc(src0, src1, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch, int B, int H,
+                                         int W, const void* wpacked, const float* bias_packed,
+                                         const float* c_prev, float* c_next, void* h_next,
+                                         void* gates_out, int ksize, void* stream) {
+    if (!x || !wpacked || !c_next || !h_next || Ch <= 0 || Cin <= 0) {
+        set_last_error("b200_convlstm_cell_fwd_tc: bad arguments");
+        return B200_ERR_ARG;
+    }
+    ConvTcParams p = {};
+    p.T = 1; p.B = B; p.H = H; p.W = W;
+    p.C0 = Cin; p.C1 = h_prev ? Ch : 0;
+    p.N = 4 * Ch; p.ksize = ksize;
+    p.wK = Cin + Ch;
+    p.bias = bias_packed;
+    p.c_prev = c_prev; p.c_next = c_next;
+    p.h_next = static_cast<__nv_bfloat16*>(h_next);
+    p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
+    // With h_prev == NULL (zero initial state, unet.py:23-25) the h half of K is skipped; the
+    // packed weight rows still span Cin+Ch columns, so the weight map must keep the full K.
+    return launch_conv_tc(x, h_prev, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
+                             int ksize, float* dw, long long ldk, int koff, void* stream) {
+    if (!dz || !src || !dw || Nz <= 0 || Csrc <= 0 || (ksize & 1) == 0 || koff < 0 || koff + Csrc > ldk) {
+        set_last_error("b200_wgrad_tc: bad arguments");
+        return B200_ERR_ARG;
+    }
+    return launch_wgrad_tc(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_wgrad_tc_supported(int B, int H, int W, int Nz, int Csrc) {
+    MTile mt;
+    if (!plan_mtile(B, H, W, 64, &mt)) return 0;
+    if (Nz <= 0 || Csrc <= 0 || Nz % 16 != 0 || Csrc % 16 != 0) return 0;
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic SIMT convolutions (fp32 check mode; shapes the tensor-core path cannot tile)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_conv_simt_fwd(const void* src0, int C0, const void* src1, int C1, int IMG, int H, int W,
+                                  const void* w, const float* bias, int N, int ksize, void* dst0, long long ld0,
+                                  int split, void* dst1, long long ld1, int dtype_fp32, int out_fp32, int relu,
+                                  void* stream) {
+    if (!src0 || !w || !dst0 || IMG <= 0 || H <= 0 || W <= 0 || C0 <= 0 || C1 < 0 || N <= 0 || (ksize & 1) == 0 ||
+        (C1 > 0 && !src1) || split < 0 || split > N || (split < N && !dst1)) {
+        set_last_error("b200_conv_simt_fwd: bad arguments");
+        return B200_ERR_ARG;
+    }
+    ConvSimtParams p = {};
+    p.src0 = src0; p.src1 = src1; p.w = w; p.bias = bias; p.dst0 = dst0; p.dst1 = dst1;
+    p.IMG = IMG; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.N = N; p.ksize = ksize; p.pad = ksize / 2;
+    p.split = split; p.ld0 = ld0; p.ld1 = ld1; p.relu = relu; p.out_fp32 = out_fp32 || dtype_fp32;
+    return launch_conv_simt(p, dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_wgrad_simt(const void* dz, int Nz, const void* src, int Csrc, int IMG, int H, int W, int ksize,
+                               float* dw, long long ldk, int koff, int dtype_fp32, void* stream) {
+    if (!dz || !src || !dw || Nz <= 0 || Csrc <= 0 || (ksize & 1) == 0 || koff < 0 || koff + Csrc > ldk) {
+        set_last_error("b200_wgrad_simt: bad arguments");
+        return B200_ERR_ARG;
+    }
+    WgradSimtParams p = {};
+    p.dz = dz; p.src = src; p.dw = dw; p.IMG = IMG; p.H = H; p.W = W; p.Nz = Nz; p.Csrc = Csrc;
+    p.ksize = ksize; p.pad = ksize / 2; p.ldk = ldk; p.koff = koff;
+    return launch_wgrad_simt(p, dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU
+// ------------------------------------------------------------------------------------------------
+#define B200_REQUIRE(cond, name)                          \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            set_last_error(name ": bad arguments");       \
+            return B200_ERR_ARG;                          \
+        }                                                 \
+    } while (0)
+
+extern "C" int b200_bn_stats(const void* x, int T, long long P, int C, int dtype_fp32, double* sum, double* sumsq,
+                             void* stream) {
+    B200_REQUIRE(x && sum && sumsq && T > 0 && P > 0 && C > 0, "b200_bn_stats");
+    return launch_bn_stats(x, T, P, C, dtype_fp32, sum, sumsq, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_finalize(const double* sum, const double* sumsq, int T, long long n, int C,
+                                const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                float eps, float momentum, int training, float* mean, float* rstd, float* scale,
+                                float* shift, void* stream) {
+    B200_REQUIRE(gamma && beta && running_mean && running_var && mean && rstd && scale && shift && C > 0 &&
+                     (!training || (sum && sumsq && T > 0 && n > 0)),
+                 "b200_bn_finalize");
+    return launch_bn_finalize(sum, sumsq, T, n, C, gamma, beta, running_mean, running_var, eps, momentum, training,
+                              mean, rstd, scale, shift, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_apply(const void* x, const float* scale, const float* shift, void* y, int T, long long P,
+                                  int C, int tstride, int relu, int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && scale && shift && y && T > 0 && P > 0 && C > 0, "b200_bn_relu_apply");
+    return launch_bn_relu_apply(x, scale, shift, y, T, P, C, tstride, relu, dtype_fp32,
+                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_bwd_reduce(const void* x, const void* dy, const float* mean, const float* rstd,
+                                       const float* scale, const float* shift, int T, long long P, int C,
+                                       int tstride, int dtype_fp32, double* sum_g, double* sum_gx, void* stream) {
+    B200_REQUIRE(x && dy && mean && rstd && scale && shift && sum_g && sum_gx && T > 0 && P > 0 && C > 0,
+                 "b200_bn_relu_bwd_reduce");
+    return launch_bn_relu_bwd_reduce(x, dy, mean, rstd, scale, shift, T, P, C, tstride, dtype_fp32, sum_g, sum_gx,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_bwd_finalize(const double* sum_g, const double* sum_gx, int T, long long n, int C,
+                                    int training, float* coef1, float* coef2, float* dgamma, float* dbeta,
+                                    int accumulate, void* stream) {
+    B200_REQUIRE(sum_g && sum_gx && coef1 && coef2 && dgamma && dbeta && T > 0 && n > 0 && C > 0,
+                 "b200_bn_bwd_finalize");
+    return launch_bn_bwd_finalize(sum_g, sum_gx, T, n, C, training, coef1, coef2, dgamma, dbeta, accumulate,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_bwd_apply(const void* x, const void* dy, const float* mean, const float* rstd,
+                                      const float* scale, const float* shift, const float* coef1,
+                                      const float* coef2, void* dx, int T, long long P, int C, int tstride,
+                                      int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && dy && mean && rstd && scale && shift && coef1 && coef2 && dx && T > 0 && P > 0 && C > 0,
+                 "b200_bn_relu_bwd_apply");
+    return launch_bn_relu_bwd_apply(x, dy, mean, rstd, scale, shift, coef1, coef2, dx, T, P, C, tstride, dtype_fp32,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool, ConvLSTM gate math, reductions, 1x1 output conv, pixel shuffle, strided copy
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_maxpool2_fwd(const void* x, void* y, long long IMG, int H, int W, int C, int dtype_fp32,
+                                 void* stream) {
+    B200_REQUIRE(x && y && IMG > 0 && H > 0 && W > 0 && C > 0, "b200_maxpool2_fwd");
+    return launch_maxpool2_fwd(x, y, IMG, H, W, C, dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_maxpool2_bwd(const void* x, const void* dy, void* dx, long long IMG, int H, int W, int C,
+                                 int accumulate, int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && dy && dx && IMG > 0 && H > 0 && W > 0 && C > 0, "b200_maxpool2_bwd");
+    return launch_maxpool2_bwd(x, dy, dx, IMG, H, W, C, accumulate, dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next,
+                                   long long P, int Ch, int dtype_fp32, void* stream) {
+    B200_REQUIRE(z && gates && c_next && h_next && P > 0 && Ch > 0, "b200_lstm_gates_fwd");
+    return launch_lstm_gates_fwd(z, c_prev, gates, c_next, h_next, P, Ch, dtype_fp32,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_next, const void* dh_a,
+                                   const void* dh_b, const float* dc_next, void* dz, float* dc_prev, long long P,
+                                   int Ch, int dtype_fp32, void* stream) {
+    B200_REQUIRE(gates && c_next && dz && dc_prev && P > 0 && Ch > 0, "b200_lstm_gates_bwd");
+    return launch_lstm_gates_bwd(gates, c_prev, c_next, dh_a, dh_b, dc_next, dz, dc_prev, P, Ch, dtype_fp32,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_colsum(const void* x, long long rows, int C, int dtype_fp32, double* workspace, float* out,
+                           int accumulate, void* stream) {
+    B200_REQUIRE(x && workspace && out && rows > 0 && C > 0, "b200_colsum");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = launch_colsum(x, rows, C, dtype_fp32, workspace, st);
+    if (rc != B200_OK) return rc;
+    return launch_cast_double(workspace, out, C, accumulate, st);
+}
+
+extern "C" int b200_outconv_fwd(const void* x, const float* w, const float* b, float* y, long long P, int C, int O,
+                                int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && w && y && P > 0 && C > 0 && O > 0, "b200_outconv_fwd");
+    return launch_outconv_fwd(x, w, b, y, P, C, O, dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_outconv_bwd(const void* x, const float* w, const float* dy, long long P, int C, int O,
+                                int dtype_fp32, void* dx, double* workspace, float* dw, float* db, int accumulate,
+                                void* stream) {
+    B200_REQUIRE(x && w && dy && workspace && P > 0 && C > 0 && O > 0, "b200_outconv_bwd");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = B200_OK;
+    if (dx) {
+        rc = launch_outconv_dgrad(dy, w, dx, P, C, O, dtype_fp32, st);
+        if (rc != B200_OK) return rc;
+    }
+    if (dw) {
+        for (int o = 0; o < O; ++o) {
+            rc = launch_outconv_wgrad(x, dy, P, C, O, o, dtype_fp32, workspace, st);
+            if (rc != B200_OK) return rc;
+            rc = launch_cast_double(workspace, dw + static_cast<long long>(o) * C, C, accumulate, st);
+            if (rc != B200_OK) return rc;
+        }
+    }
+    if (db) {
+        rc = launch_colsum(dy, P, O, 1, workspace, st);
+        if (rc != B200_OK) return rc;
+        rc = launch_cast_double(workspace, db, O, accumulate, st);
+    }
+    return rc;
+}
+
+extern "C" int b200_shuffle2x2(const void* src, void* dst, const float* bias, long long IMG, int H, int W, int C,
+                               int Hd, int Wd, int oy, int ox, int unshuffle, int dtype_fp32, void* stream) {
+    B200_REQUIRE(src && dst && IMG > 0 && H > 0 && W > 0 && C > 0 && Hd > 0 && Wd > 0, "b200_shuffle2x2");
+    return launch_shuffle2x2(src, dst, bias, IMG, H, W, C, Hd, Wd, oy, ox, unshuffle, dtype_fp32,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_strided_copy(const void* src, int src_fp32, void* dst, int dst_fp32, const long long* dims,
+                                 const long long* src_strides, const long long* dst_strides, int accumulate,
+                                 void* stream) {
+    B200_REQUIRE(src && dst && dims && src_strides && dst_strides, "b200_strided_copy");
+    for (int i = 0; i < 5; ++i)
+        if (dims[i] < 0) {
+            set_last_error("b200_strided_copy: negative dimension");
+            return B200_ERR_ARG;
+        }
+    return launch_strided_copy(src, src_fp32, dst, dst_fp32, dims, src_strides, dst_strides, accumulate,
+                               static_cast<cudaStream_t>(stream));
+}

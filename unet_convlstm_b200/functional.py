@@ -1,0 +1,321 @@
+"""Autograd functions of the hot path on NHWC sequence tensors [T, B, H, W, C].
+
+Each Function's forward/backward is a short sequence of launches of our CUDA kernels (ops.py);
+the backward formulas are the hand-derived autograd of the reference modules in train/unet.py
+(dordanino12/unet-convlstm), cited per class.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class WeightCache:
+    """Packed (GEMM-layout, activation-dtype) copies of a module's parameters, rebuilt when the
+    parameter changes (optimizer step / load_state_dict bump the tensor version)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, key, params, builder):
+        ver = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = builder()
+        self._d[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._d.clear()
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# layout changes at the module boundary (reference tensors are NCHW fp32)
+# ------------------------------------------------------------------------------------------------
+class PermuteCast(torch.autograd.Function):
+    """y = x.permute(perm) as a contiguous tensor of `dtype`, last dim zero-padded to `pad_to`."""
+
+    @staticmethod
+    def forward(ctx, x, perm, dtype, pad_to):
+        xv = x.permute(*perm)
+        C = xv.shape[-1]
+        Cp = C if pad_to is None else max(C, pad_to)
+        shape = tuple(xv.shape[:-1]) + (Cp,)
+        y = (torch.zeros if Cp != C else torch.empty)(shape, device=x.device, dtype=dtype)
+        ops.copy_(y[..., :C], xv)
+        ctx.perm, ctx.C, ctx.xdtype, ctx.xshape = perm, C, x.dtype, x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        inv = [0] * len(ctx.perm)
+        for i, p in enumerate(ctx.perm):
+            inv[p] = i
+        dx = torch.empty(ctx.xshape, device=dy.device, dtype=ctx.xdtype)
+        ops.copy_(dx, dy[..., :ctx.C].permute(*inv))
+        return dx, None, None, None
+
+
+def permute_cast(x, perm, dtype, pad_to=None):
+    return PermuteCast.apply(x, tuple(perm), dtype, pad_to)
+
+
+# ------------------------------------------------------------------------------------------------
+# conv3x3 + BatchNorm + ReLU (one half of DoubleConv, unet.py:66-75)
+# ------------------------------------------------------------------------------------------------
+class ConvBnRelu(torch.autograd.Function):
+    """y = relu(bn(conv3x3([x0 ; x1]) + bias)).  The channel concat of Up (unet.py:98) is virtual:
+    the GEMM K loop reads x0 then x1.  BatchNorm statistics are per timestep (unet.py:179-182)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, momentum, cache):
+        x0 = _c(x0)
+        x1 = None if x1 is None else _c(x1)
+        dt = x0.dtype
+        T, B, H, W, C0 = x0.shape
+        C1 = 0 if x1 is None else x1.shape[-1]
+        N, K = weight.shape[0], weight.shape[1]
+        ks = weight.shape[2]
+        if K > C0 + C1 or (x1 is not None and K != C0 + C1):
+            raise ValueError(f"conv weight expects {K} input channels, got {C0}+{C1}")
+        wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
+        z = torch.empty((T, B, H, W, N), device=x0.device, dtype=dt)
+        ops.conv_fwd(x0, x1, wp, bias.detach() if bias is not None else None, ks, z)
+        y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum)
+        ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
+        ctx.tstride = stats[4]
+        ctx.training, ctx.cache, ctx.has_bias = training, cache, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x0, x1, z, weight, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        dt = z.dtype
+        dy = _c(dy)
+        if dy.dtype != dt:
+            dy = dy.to(dt)
+        T, B, H, W, N = z.shape
+        C0 = x0.shape[-1]
+        C1 = 0 if x1 is None else x1.shape[-1]
+        K, ks = weight.shape[1], weight.shape[2]
+        dz, dgamma, dbeta = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training)
+        dbias = ops.colsum(T * B * H * W, dz, N) if ctx.has_bias else None
+        # weight gradient, batched over all T*B images
+        dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
+        ops.conv_wgrad(dz, x0, ks, dwp, 0)
+        if x1 is not None:
+            ops.conv_wgrad(dz, x1, ks, dwp, C0)
+        dweight = ops.unpack_conv_wgrad(dwp, K)
+        # data gradient, split over the two sources of the virtual concat
+        dx0 = dx1 = None
+        need0, need1 = ctx.needs_input_grad[0], (x1 is not None and ctx.needs_input_grad[1])
+        if need0 or need1:
+            wd = ctx.cache.get(("dgrad", dt, C0 + C1), (weight,),
+                               lambda: _dgrad_pack_padded(weight, dt, C0 + C1))
+            dx0 = torch.empty_like(x0)
+            dx1 = torch.empty_like(x1) if x1 is not None else None
+            ops.conv_fwd(dz, None, wd, None, ks, dx0, dx1)
+        return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
+
+
+def _dgrad_pack_padded(weight, dt, Kp):
+    """Data-gradient weights [taps, Kp, N]; rows >= K (zero-padded input channels) stay zero."""
+    N, K = weight.shape[0], weight.shape[1]
+    if Kp == K:
+        return ops.pack_conv_weight_dgrad(weight, dt)
+    full = torch.zeros((weight.shape[2] * weight.shape[3], Kp, N), device=weight.device, dtype=dt)
+    packed = ops.pack_conv_weight_dgrad(weight, dt)
+    ops.copy_(full[:, :K, :], packed)
+    return full
+
+
+# ------------------------------------------------------------------------------------------------
+# 2x2 max-pool (Down, unet.py:78-84)
+# ------------------------------------------------------------------------------------------------
+class MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = ops.maxpool2_fwd(x)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, _c(dy).to(x.dtype))
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvTranspose2d(k=2, stride=2) + F.pad to the skip size (Up, unet.py:90-97)
+# ------------------------------------------------------------------------------------------------
+class ConvT2x2(torch.autograd.Function):
+    """A GEMM [P, Cin] x [Cin, 4*Cout] followed by a pixel shuffle (each input pixel produces a 2x2
+    output patch, no overlap)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, Hd, Wd, cache):
+        x = _c(x)
+        dt = x.dtype
+        T, B, H, W, Cin = x.shape
+        Cout = weight.shape[1]
+        wf, _ = cache.get(("convT", dt), (weight,), lambda: ops.pack_convT_weight(weight, dt))
+        z = torch.empty((T, B, H, W, 4 * Cout), device=x.device, dtype=dt)
+        ops.conv_fwd(x, None, wf, None, 1, z)
+        y = ops.shuffle2x2(z, bias.detach() if bias is not None else None, Hd, Wd)
+        ctx.save_for_backward(x, weight)
+        ctx.cache, ctx.has_bias = cache, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dt = x.dtype
+        T, B, H, W, Cin = x.shape
+        Cout = weight.shape[1]
+        du = ops.unshuffle2x2(_c(dy).to(dt), H, W)  # [T,B,H,W,4*Cout]
+        dbias = ops.colsum(T * B * H * W * 4, du, Cout) if ctx.has_bias else None
+        dwp = torch.zeros((1, 4 * Cout, Cin), device=x.device, dtype=torch.float32)
+        ops.conv_wgrad(du, x, 1, dwp, 0)
+        dweight = torch.empty_like(weight)
+        ops.copy_(dweight.view(Cin, Cout, 4), dwp.view(4, Cout, Cin).permute(2, 1, 0))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wb = ctx.cache.get(("convT", dt), (weight,), lambda: ops.pack_convT_weight(weight, dt))
+            dx = torch.empty_like(x)
+            ops.conv_fwd(du, None, wb, None, 1, dx)
+        return dx, dweight, dbias, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# 1x1 output convolution (OutConv, unet.py:101-107), fp32 output
+# ------------------------------------------------------------------------------------------------
+class OutConv1x1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        w2 = weight.detach().reshape(weight.shape[0], weight.shape[1])
+        y = ops.outconv_fwd(x, w2, bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        w2 = weight.detach().reshape(weight.shape[0], weight.shape[1])
+        dx, dw, db = ops.outconv_bwd(x, w2, _c(dy).float(), ctx.needs_input_grad[0])
+        return dx, dw.view_as(weight), (db if ctx.has_bias else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvLSTM layer over a whole sequence (ConvLSTMCell + the t-loop of ConvLSTM, unet.py:14-60)
+# ------------------------------------------------------------------------------------------------
+class ConvLSTMSeq(torch.autograd.Function):
+    """h_seq, c_T = ConvLSTM layer(x_seq, h0, c0).
+
+    Forward, per timestep: one fused kernel -- implicit-GEMM gate conv over the virtual concat
+    [x_t ; h_{t-1}] on tcgen05 with the sigmoid/tanh gate math and the c/h update in the epilogue --
+    or, in the fp32 check mode / for shapes the tensor-core path cannot tile, a CUDA-core conv plus
+    the gate-math kernel.  h_t (activation dtype), c_t (fp32) and the activated gates are kept for BPTT.
+    Backward: for t = T-1..0 the gate-gradient kernel and the data-gradient conv ([dx_t ; dh_{t-1}]);
+    the weight gradient is ONE reduction over all T*B*H*W pixels after the sweep."""
+
+    @staticmethod
+    def forward(ctx, x_seq, h0, c0, weight, bias, cache):
+        x_seq = _c(x_seq)
+        dt = x_seq.dtype
+        T, B, H, W, Cin = x_seq.shape
+        Ch = weight.shape[0] // 4
+        ks = weight.shape[2]
+        dev = x_seq.device
+        if weight.shape[1] != Cin + Ch:
+            raise ValueError(f"ConvLSTM weight expects {weight.shape[1]} input channels, got {Cin}+{Ch}")
+        fused = ops.lstm_tc_ok(x_seq[0], Ch)
+        h_all = torch.empty((T + 1, B, H, W, Ch), device=dev, dtype=dt)
+        c_all = torch.empty((T + 1, B, H, W, Ch), device=dev, dtype=torch.float32)
+        gates = torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
+        have_h0 = h0 is not None
+        if have_h0:
+            ops.copy_(h_all[0], h0.detach())
+            ops.copy_(c_all[0], c0.detach())
+        elif not fused:
+            h_all[0].zero_()
+        if fused:
+            wp, bp = cache.get(("lstm", dt), (weight, bias), lambda: ops.pack_lstm_weight(weight, bias, dt))
+            for t in range(T):
+                first_zero = (t == 0 and not have_h0)
+                ops.lstm_cell_fwd_fused(x_seq[t], None if first_zero else h_all[t], None if first_zero else c_all[t],
+                                        wp, bp, c_all[t + 1], h_all[t + 1], gates[t], ks)
+        else:
+            wp = cache.get(("fwd", dt, Cin + Ch), (weight,), lambda: ops.pack_conv_weight(weight, dt))
+            zbuf = torch.empty((B, H, W, 4 * Ch), device=dev, dtype=torch.float32)
+            bd = bias.detach() if bias is not None else None
+            for t in range(T):
+                first_zero = (t == 0 and not have_h0)
+                ops.lstm_cell_fwd_unfused(x_seq[t], h_all[t], None if first_zero else c_all[t], wp, bd,
+                                          c_all[t + 1], h_all[t + 1], gates[t], ks, zbuf)
+        ctx.save_for_backward(x_seq, weight)
+        ctx.h_all, ctx.c_all, ctx.gates = h_all, c_all, gates
+        ctx.have_h0, ctx.cache, ctx.has_bias = have_h0, cache, bias is not None
+        h_seq = h_all[1:]
+        c_T = c_all[T]
+        ctx.mark_non_differentiable()
+        return h_seq, c_T
+
+    @staticmethod
+    def backward(ctx, dh_seq, dc_T):
+        x_seq, weight = ctx.saved_tensors
+        h_all, c_all, gates = ctx.h_all, ctx.c_all, ctx.gates
+        dt = x_seq.dtype
+        T, B, H, W, Cin = x_seq.shape
+        Ch = weight.shape[0] // 4
+        ks = weight.shape[2]
+        dev = x_seq.device
+        dh_seq = None if dh_seq is None else _c(dh_seq).to(dt)
+        dc_next = None if dc_T is None else _c(dc_T).float()
+        wd = ctx.cache.get(("dgrad", dt, Cin + Ch), (weight,), lambda: ops.pack_conv_weight_dgrad(weight, dt))
+        dz_all = torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
+        need_dx = ctx.needs_input_grad[0]
+        dx_seq = torch.empty_like(x_seq) if need_dx else None
+        dx_scratch = None if need_dx else torch.empty_like(x_seq[0])
+        dh_rec = [torch.empty((B, H, W, Ch), device=dev, dtype=dt) for _ in range(2)]
+        dc_buf = [torch.empty((B, H, W, Ch), device=dev, dtype=torch.float32) for _ in range(2)]
+        dh_b = None
+        for t in reversed(range(T)):
+            zero_prev = (t == 0 and not ctx.have_h0)
+            ops.lstm_gates_bwd(gates[t], None if zero_prev else c_all[t], c_all[t + 1],
+                               None if dh_seq is None else dh_seq[t], dh_b, dc_next, dz_all[t], dc_buf[t & 1])
+            dc_next = dc_buf[t & 1]
+            need_dh_prev = t > 0 or (ctx.have_h0 and (ctx.needs_input_grad[1]))
+            if need_dh_prev:
+                dxt = dx_seq[t] if need_dx else dx_scratch
+                ops.conv_fwd(dz_all[t].unsqueeze(0), None, wd, None, ks, dxt.unsqueeze(0), dh_rec[t & 1].unsqueeze(0))
+                dh_b = dh_rec[t & 1]
+            elif need_dx:
+                # only the x columns of the data gradient are needed at t = 0 with a zero initial state
+                ops.conv_fwd(dz_all[t].unsqueeze(0), None, wd[:, :Cin, :].contiguous(), None, ks,
+                             dx_seq[t].unsqueeze(0))
+        # weight / bias gradients: one reduction over the whole sequence
+        dwp = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=dev, dtype=torch.float32)
+        ops.conv_wgrad(dz_all, x_seq, ks, dwp, 0)
+        if ctx.have_h0:
+            ops.conv_wgrad(dz_all, h_all[:T], ks, dwp, Cin)
+        elif T > 1:
+            ops.conv_wgrad(dz_all[1:], h_all[1:T], ks, dwp, Cin)  # h_{-1} = 0 contributes nothing
+        dweight = ops.unpack_conv_wgrad(dwp, Cin + Ch)
+        dbias = ops.colsum(T * B * H * W, dz_all, 4 * Ch) if ctx.has_bias else None
+        dh0 = dc0 = None
+        if ctx.have_h0:
+            if ctx.needs_input_grad[1]:
+                dh0 = dh_b
+            if ctx.needs_input_grad[2]:
+                dc0 = dc_next
+        ctx.h_all = ctx.c_all = ctx.gates = None
+        return dx_seq, dh0, dc0, dweight, dbias, None

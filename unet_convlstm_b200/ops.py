@@ -1,0 +1,376 @@
+"""Tensor-level wrappers over the C ABI (include/b200_convlstm.h).
+
+torch is used here for device memory (torch.empty / torch.zeros), strides and the current stream
+only; every arithmetic kernel is one of ours.  Activations are NHWC: a sequence tensor is
+[T, B, H, W, C] (contiguous); P = B*H*W pixels per timestep.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+# ------------------------------------------------------------------------------------------------
+# precision mode
+# ------------------------------------------------------------------------------------------------
+_PRECISION = os.environ.get("B200_PRECISION", "bf16")
+
+
+def set_precision(mode: str) -> None:
+    """'bf16': tcgen05 tensor-core path, bf16 activations, fp32 accumulation and cell state.
+    'fp32': check mode -- fp32 storage and CUDA-core FMA convolutions (1e-5 parity with the reference)."""
+    global _PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError(f"unknown precision mode {mode!r}")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def act_dtype() -> torch.dtype:
+    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t) -> int:
+    if t.dtype == torch.float32:
+        return 1
+    if t.dtype == torch.bfloat16:
+        return 0
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _chk(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: the B200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor, got strides {t.stride()}")
+    return t
+
+
+_LL5 = ctypes.c_longlong * 5
+
+
+def _copy_raw(dst, dst_off, src, src_off, dims, accumulate=False):
+    """dims: list of (n, src_stride, dst_stride) in elements (strides may be negative)."""
+    dims = [d for d in dims if d[0] != 1]
+    merged = []
+    for n, ss, ds in dims:
+        if merged:
+            pn, pss, pds = merged[-1]
+            if pss == ss * n and pds == ds * n:
+                merged[-1] = (pn * n, ss, ds)
+                continue
+        merged.append((n, ss, ds))
+    if len(merged) > 5:
+        raise ValueError("copy_: more than 5 non-mergeable dimensions")
+    # iterate with the smallest destination stride innermost (coalesced writes)
+    merged.sort(key=lambda d: -abs(d[2]))
+    while len(merged) < 5:
+        merged.insert(0, (1, 0, 0))
+    _lib.call("b200_strided_copy", src.data_ptr() + src_off * src.element_size(), _f32(src),
+              dst.data_ptr() + dst_off * dst.element_size(), _f32(dst),
+              _LL5(*[d[0] for d in merged]), _LL5(*[d[1] for d in merged]), _LL5(*[d[2] for d in merged]),
+              int(accumulate), _st())
+
+
+def copy_(dst: torch.Tensor, src: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    """dst (+)= src for two equally-shaped, arbitrarily strided views (fp32 / bf16, converting)."""
+    if tuple(dst.shape) != tuple(src.shape):
+        raise ValueError(f"copy_: shape mismatch {tuple(dst.shape)} vs {tuple(src.shape)}")
+    if not (dst.is_cuda and src.is_cuda):
+        raise RuntimeError("copy_: the B200 kernels need CUDA tensors (there is no CPU fallback)")
+    if dst.numel() == 0:
+        return dst
+    _copy_raw(dst, 0, src, 0, list(zip(src.shape, src.stride(), dst.stride())), accumulate)
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (all through the strided-copy kernel)
+# ------------------------------------------------------------------------------------------------
+def lstm_cht(Ch: int) -> int:
+    """Hidden channels per GEMM N tile of the fused cell kernel (conv_tc.cu pick_block_n)."""
+    return 64 if Ch % 64 == 0 else (32 if Ch % 32 == 0 else (16 if Ch % 16 == 0 else 0))
+
+
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, kpad: int | None = None) -> torch.Tensor:
+    """OIHW fp32 [N, K, k, k] -> [k*k, N, Kp] (K contiguous: the GEMM B operand, K-major)."""
+    N, K, kh, kw = w.shape
+    taps = kh * kw
+    Kp = K if kpad is None else kpad
+    out = (torch.zeros if Kp != K else torch.empty)((taps, N, Kp), device=w.device, dtype=dtype)
+    copy_(out[:, :, :K], w.detach().reshape(N, K, taps).permute(2, 0, 1))
+    return out
+
+
+def pack_conv_weight_dgrad(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """OIHW [N, K, k, k] -> [k*k (flipped), K, N]: the weights of the data-gradient convolution."""
+    N, K, kh, kw = w.shape
+    taps = kh * kw
+    out = torch.empty((taps, K, N), device=w.device, dtype=dtype)
+    # out[taps-1-tap][k][n] = w[n][k][tap]: the tap dimension runs backwards in the destination
+    _copy_raw(out, (taps - 1) * K * N, w.detach(), 0,
+              [(taps, 1, -K * N), (K, taps, N), (N, K * taps, 1)])
+    return out
+
+
+def pack_lstm_weight(w: torch.Tensor, b: torch.Tensor | None, dtype: torch.dtype):
+    """Gate-interleaved packing for the fused cell kernel: packed row (nt*4 + g)*CHT + j holds
+    reference row g*Ch + nt*CHT + j (rows blocked i,f,g,o: unet.py:19,29)."""
+    N, K, kh, kw = w.shape
+    Ch, taps = N // 4, kh * kw
+    cht = lstm_cht(Ch)
+    nt = Ch // cht
+    out = torch.empty((taps, N, K), device=w.device, dtype=dtype)
+    # views [taps, nt, g, j, K]
+    dst = out.view(taps, nt, 4, cht, K)
+    src = w.detach().reshape(4, nt, cht, K, taps).permute(4, 1, 0, 2, 3)
+    copy_(dst, src)
+    bp = None
+    if b is not None:
+        bp = torch.empty(N, device=w.device, dtype=torch.float32)
+        copy_(bp.view(nt, 4, cht), b.detach().reshape(4, nt, cht).permute(1, 0, 2))
+    return out, bp
+
+
+def pack_convT_weight(w: torch.Tensor, dtype: torch.dtype):
+    """ConvTranspose2d weight IOHW [Cin, Cout, 2, 2] -> forward GEMM B operand [1, 4*Cout (tap, co), Cin]
+    and data-gradient operand [1, Cin, 4*Cout]."""
+    Cin, Cout = w.shape[0], w.shape[1]
+    fwd = torch.empty((1, 4 * Cout, Cin), device=w.device, dtype=dtype)
+    copy_(fwd.view(4, Cout, Cin), w.detach().reshape(Cin, Cout, 4).permute(2, 1, 0))
+    bwd = torch.empty((1, Cin, 4 * Cout), device=w.device, dtype=dtype)
+    copy_(bwd.view(Cin, 4, Cout), w.detach().reshape(Cin, Cout, 4).permute(0, 2, 1))
+    return fwd, bwd
+
+
+def unpack_conv_wgrad(dw: torch.Tensor, K: int) -> torch.Tensor:
+    """[taps, N, Kp] fp32 -> OIHW [N, K, k, k] fp32."""
+    taps, N, Kp = dw.shape
+    k = int(round(taps ** 0.5))
+    g = torch.empty((N, K, k, k), device=dw.device, dtype=torch.float32)
+    copy_(g.view(N, K, taps), dw[:, :, :K].permute(1, 2, 0))
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions
+# ------------------------------------------------------------------------------------------------
+def tc_conv_ok(x0, x1, N, lstm=False) -> bool:
+    if x0.dtype != torch.bfloat16:
+        return False
+    T, B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    return _lib.supported("b200_conv_tc_supported", B, H, W, C0, C1, N, int(lstm))
+
+
+def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False):
+    """out = conv_k([x0 ; x1]) (+bias) (+relu).  x*: [T,B,H,W,C*]; wp: [k*k, N, C0+C1]; the N output
+    columns go to out0 (its last dim) and, if given, the rest to out1 (dgrad of a virtual concat)."""
+    _chk(x0, "x0"), _chk(wp, "wp"), _chk(out0, "out0")
+    T, B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else _chk(x1, "x1").shape[-1]
+    N = wp.shape[1]
+    split = out0.shape[-1]
+    if wp.shape[2] != C0 + C1 or wp.dtype != x0.dtype:
+        raise ValueError(f"conv_fwd: packed weights {tuple(wp.shape)}/{wp.dtype} do not match C0+C1={C0 + C1}/{x0.dtype}")
+    if split + (0 if out1 is None else out1.shape[-1]) != N:
+        raise ValueError("conv_fwd: output widths do not add up to N")
+    if out1 is not None and out1.dtype != out0.dtype:
+        raise ValueError("conv_fwd: out0/out1 dtypes differ")
+    ld1 = 0 if out1 is None else out1.shape[-1]
+    if tc_conv_ok(x0, x1, N) and split % 16 == 0 and out0.shape[-1] % 8 == 0 and ld1 % 8 == 0:
+        _lib.call("b200_conv_tc_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(bias), N, ksize, _p(out0),
+                  out0.shape[-1], split, _p(out1), ld1, _f32(out0), int(relu), 0, _st())
+    else:
+        _lib.call("b200_conv_simt_fwd", _p(x0), C0, _p(x1), C1, T * B, H, W, _p(wp), _p(bias), N, ksize,
+                  _p(out0), out0.shape[-1], split, _p(out1), ld1, _f32(x0), _f32(out0), int(relu), _st())
+    return out0
+
+
+def conv_wgrad(dz, src, ksize, dw, koff):
+    """dw[tap][n][koff + c] += sum_{t,p} dz[t,p,n] * src[t,p+tap,c]; dw fp32 [k*k, Nz, ldk] (pre-zeroed)."""
+    _chk(dz, "dz"), _chk(src, "src"), _chk(dw, "dw")
+    T, B, H, W, Nz = dz.shape
+    Cs = src.shape[-1]
+    ldk = dw.shape[2]
+    if dz.dtype == torch.bfloat16 and ldk % 4 == 0 and koff % 4 == 0 and \
+            _lib.supported("b200_wgrad_tc_supported", B, H, W, Nz, Cs):
+        _lib.call("b200_wgrad_tc", _p(dz), Nz, _p(src), Cs, T, B, H, W, ksize, _p(dw), ldk, koff, _st())
+    else:
+        _lib.call("b200_wgrad_simt", _p(dz), Nz, _p(src), Cs, T * B, H, W, ksize, _p(dw), ldk, koff, _f32(dz), _st())
+    return dw
+
+
+def colsum(x2d_rows: int, x, C: int, out=None, accumulate=False):
+    """out[c] (+)= sum over rows of x viewed as [rows, C]."""
+    ws = torch.empty(C, device=x.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty(C, device=x.device, dtype=torch.float32)
+    _lib.call("b200_colsum", _p(x), x2d_rows, C, _f32(x), _p(ws), _p(out), int(accumulate), _st())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm + ReLU
+# ------------------------------------------------------------------------------------------------
+def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum):
+    """Returns (y, stats) with stats = (mean, rstd, scale, shift, tstride); statistics per (t, c)."""
+    _chk(z, "z")
+    T, B, H, W, C = z.shape
+    P = B * H * W
+    dev = z.device
+    Ts = T if training else 1
+    mean = torch.empty((Ts, C), device=dev, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    scale = torch.empty_like(mean)
+    shift = torch.empty_like(mean)
+    if training:
+        ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
+        _lib.call("b200_bn_stats", _p(z), T, P, C, _f32(z), _p(ws[0]), _p(ws[1]), _st())
+        _lib.call("b200_bn_finalize", _p(ws[0]), _p(ws[1]), T, P, C, _p(gamma), _p(beta), _p(running_mean),
+                  _p(running_var), eps, momentum, 1, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
+    else:
+        _lib.call("b200_bn_finalize", None, None, 1, P, C, _p(gamma), _p(beta), _p(running_mean),
+                  _p(running_var), eps, momentum, 0, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
+    tstride = C if training else 0
+    y = torch.empty_like(z)
+    _lib.call("b200_bn_relu_apply", _p(z), _p(scale), _p(shift), _p(y), T, P, C, tstride, 1, _f32(z), _st())
+    return y, (mean, rstd, scale, shift, tstride)
+
+
+def bn_relu_bwd(z, dy, stats, training):
+    """Returns (dz, dgamma, dbeta)."""
+    _chk(z, "z"), _chk(dy, "dy")
+    mean, rstd, scale, shift, tstride = stats
+    T, B, H, W, C = z.shape
+    P = B * H * W
+    dev = z.device
+    ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
+    _lib.call("b200_bn_relu_bwd_reduce", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), T, P, C, tstride,
+              _f32(z), _p(ws[0]), _p(ws[1]), _st())
+    coef = torch.empty((2, T, C), device=dev, dtype=torch.float32)
+    dgamma = torch.empty(C, device=dev, dtype=torch.float32)
+    dbeta = torch.empty(C, device=dev, dtype=torch.float32)
+    _lib.call("b200_bn_bwd_finalize", _p(ws[0]), _p(ws[1]), T, P, C, int(training), _p(coef[0]), _p(coef[1]),
+              _p(dgamma), _p(dbeta), 0, _st())
+    dz = torch.empty_like(z)
+    _lib.call("b200_bn_relu_bwd_apply", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), _p(coef[0]),
+              _p(coef[1]), _p(dz), T, P, C, tstride, _f32(z), _st())
+    return dz, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------
+# max-pool, pixel shuffle, 1x1 output conv
+# ------------------------------------------------------------------------------------------------
+def maxpool2_fwd(x):
+    _chk(x, "x")
+    T, B, H, W, C = x.shape
+    y = torch.empty((T, B, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
+    _lib.call("b200_maxpool2_fwd", _p(x), _p(y), T * B, H, W, C, _f32(x), _st())
+    return y
+
+
+def maxpool2_bwd(x, dy):
+    _chk(x, "x"), _chk(dy, "dy")
+    T, B, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("b200_maxpool2_bwd", _p(x), _p(dy), _p(dx), T * B, H, W, C, 0, _f32(x), _st())
+    return dx
+
+
+def shuffle2x2(z, bias, Hd, Wd):
+    """z [T,B,H,W,4*C] (tap-major columns) -> y [T,B,Hd,Wd,C] (+bias), centred like F.pad (unet.py:95-97)."""
+    _chk(z, "z")
+    T, B, H, W, C4 = z.shape
+    C = C4 // 4
+    oy, ox = (Hd - 2 * H) // 2, (Wd - 2 * W) // 2
+    exact = (Hd == 2 * H and Wd == 2 * W)
+    y = (torch.empty if exact else torch.zeros)((T, B, Hd, Wd, C), device=z.device, dtype=z.dtype)
+    _lib.call("b200_shuffle2x2", _p(z), _p(y), _p(bias), T * B, H, W, C, Hd, Wd, oy, ox, 0, _f32(z), _st())
+    return y
+
+
+def unshuffle2x2(dy, H, W):
+    _chk(dy, "dy")
+    T, B, Hd, Wd, C = dy.shape
+    oy, ox = (Hd - 2 * H) // 2, (Wd - 2 * W) // 2
+    du = torch.empty((T, B, H, W, 4 * C), device=dy.device, dtype=dy.dtype)
+    _lib.call("b200_shuffle2x2", _p(dy), _p(du), None, T * B, H, W, C, Hd, Wd, oy, ox, 1, _f32(dy), _st())
+    return du
+
+
+def outconv_fwd(x, w, b):
+    """x [T,B,H,W,C], w fp32 [O,C] -> y fp32 [T,B,H,W,O]."""
+    _chk(x, "x")
+    T, B, H, W, C = x.shape
+    O = w.shape[0]
+    y = torch.empty((T, B, H, W, O), device=x.device, dtype=torch.float32)
+    _lib.call("b200_outconv_fwd", _p(x), _p(w), _p(b), _p(y), T * B * H * W, C, O, _f32(x), _st())
+    return y
+
+
+def outconv_bwd(x, w, dy, need_dx=True):
+    _chk(x, "x"), _chk(dy, "dy")
+    T, B, H, W, C = x.shape
+    O = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    ws = torch.empty(max(C, O), device=x.device, dtype=torch.float64)
+    dw = torch.empty((O, C), device=x.device, dtype=torch.float32)
+    db = torch.empty(O, device=x.device, dtype=torch.float32)
+    _lib.call("b200_outconv_bwd", _p(x), _p(w), _p(dy), T * B * H * W, C, O, _f32(x), _p(dx), _p(ws), _p(dw), _p(db),
+              0, _st())
+    return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvLSTM cell
+# ------------------------------------------------------------------------------------------------
+def lstm_tc_ok(x_t, Ch) -> bool:
+    if x_t.dtype != torch.bfloat16:
+        return False
+    B, H, W, Cin = x_t.shape
+    return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
+
+
+def lstm_cell_fwd_fused(x_t, h_prev, c_prev, wp_il, bias_il, c_next, h_next, gates, ksize):
+    """One fused cell step on the tensor cores (gate conv + gate math + state update)."""
+    B, H, W, Cin = x_t.shape
+    Ch = c_next.shape[-1]
+    _lib.call("b200_convlstm_cell_fwd_tc", _p(x_t), Cin, _p(h_prev), Ch, B, H, W, _p(wp_il), _p(bias_il),
+              _p(c_prev), _p(c_next), _p(h_next), _p(gates), ksize, _st())
+
+
+def lstm_cell_fwd_unfused(x_t, h_prev, c_prev, wp, bias, c_next, h_next, gates, ksize, zbuf):
+    """Generic path: CUDA-core gate conv into fp32 pre-activations, then the gate-math kernel."""
+    B, H, W, Cin = x_t.shape
+    Ch = c_next.shape[-1]
+    if h_prev is None:
+        # zero initial state (unet.py:23-25): only the x columns of the packed weights contribute
+        raise RuntimeError("lstm_cell_fwd_unfused needs an explicit h_prev")
+    _lib.call("b200_conv_simt_fwd", _p(x_t), Cin, _p(h_prev), Ch, B, H, W, _p(wp), _p(bias), 4 * Ch, ksize,
+              _p(zbuf), 4 * Ch, 4 * Ch, None, 0, _f32(x_t), 1, 0, _st())
+    _lib.call("b200_lstm_gates_fwd", _p(zbuf), _p(c_prev), _p(gates), _p(c_next), _p(h_next), B * H * W, Ch,
+              _f32(x_t), _st())
+
+
+def lstm_gates_bwd(gates, c_prev, c_next, dh_a, dh_b, dc_next, dz, dc_prev):
+    B, H, W, Ch = c_next.shape
+    _lib.call("b200_lstm_gates_bwd", _p(gates), _p(c_prev), _p(c_next), _p(dh_a), _p(dh_b), _p(dc_next), _p(dz),
+              _p(dc_prev), B * H * W, Ch, _f32(gates), _st())
