@@ -116,7 +116,7 @@ class _StripDict:
         return self.d.get(k[2:], default)
 
 
-@pytest.mark.parametrize("name", ["model_b4_skip.npz", "model_b2_noskip_l2.npz"])
+@pytest.mark.parametrize("name", ["model_b4_skip.npz", "model_b2_noskip_l2.npz", "model_b4_skip_64.npz"])
 def test_model_matches_reference(golden_dir, name):
     z, p = load(golden_dir, name)
     base_ch, skip, L, B, T, H, W = z["meta"]
@@ -149,4 +149,4 @@ def test_model_matches_reference(golden_dir, name):
 
 
 def test_fixture_set_is_complete(golden_dir):
-    assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 9
+    assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 10
