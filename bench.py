@@ -1,0 +1,352 @@
+"""Benchmark of the UNet-ConvLSTM training step (BASELINE.json metric: train sequences/s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): Moving-MNIST-shaped sequences 64x64, T=20, batch 256 per GPU,
+TemporalUNetDualView(base_ch=64, use_skip_lstm=True) -- the authors' width (reference main.py:225-226) --
+bf16 tensor-core mode.  One step = forward + backward + AdamW update (fused) on one batch; with N GPUs
+the batch of sequences is sharded data-parallel (weak scaling, 256 sequences per GPU) and gradients
+are all-reduced over NCCL, overlapped with backward.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step through the public
+nn.Module API with the batch in pinned host memory (H2D inside the timed region, loss read back).
+`roofline`: the fused ConvLSTM gate-conv kernel, timed per launch with CUDA events inside the timed
+region.  `cpu_baseline`: the reference's CPU path (oracle/torch_port.py: the reference's own ATen
+operators, functional restatement) on this box's host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train sequences/sec (fwd+bwd)"
+UNIT = "sequences/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic Moving-MNIST-shaped data (mirrors digits/build_moving_mnist.py:5-58 without the download):
+# two 28x28 blobs with integer velocities bouncing off the borders; channel 1 is the same frame as
+# seen one pixel to the right ("second satellite"); target = per-pixel x-velocity of the blobs / 10
+# ------------------------------------------------------------------------------------------------
+def make_batch(B, T, S, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:28, 0:28]
+    X = np.zeros((B, T, 2, S, S), dtype=np.float32)
+    Y = np.zeros((B, T, 1, S, S), dtype=np.float32)
+    for b in range(B):
+        for _ in range(2):
+            cx, cy, sg = rng.uniform(9, 19), rng.uniform(9, 19), rng.uniform(3, 6)
+            blob = np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * sg * sg)).astype(np.float32)
+            blob[blob < 0.35] = 0.0
+            px, py = rng.integers(0, S - 28, size=2)
+            vx, vy = rng.integers(-5, 6, size=2)
+            for t in range(T):
+                X[b, t, 0, py:py + 28, px:px + 28] = np.maximum(X[b, t, 0, py:py + 28, px:px + 28], blob)
+                Y[b, t, 0, py:py + 28, px:px + 28] += (blob > 0) * (vx / 10.0)
+                nx, ny = px + vx, py + vy
+                if nx < 0 or nx > S - 28:
+                    vx = -vx
+                    nx = px + vx
+                if ny < 0 or ny > S - 28:
+                    vy = -vy
+                    ny = py + vy
+                px, py = int(nx), int(ny)
+    X[:, :, 1, :, 1:] = X[:, :, 0, :, :-1]
+    return torch.from_numpy(X), torch.from_numpy(np.clip(Y, -1, 1))
+
+
+# ------------------------------------------------------------------------------------------------
+def clocks_sampler_start(gpu_index, path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        f = open(path, "w")
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                 "-i", str(gpu_index)], stdout=f, stderr=subprocess.DEVNULL), f
+    except OSError:
+        return None, None
+
+
+def clocks_summary(proc, f, path):
+    if proc is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    proc.terminate()
+    try:
+        proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+    f.close()
+    sm, smax, reasons = [], None, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in open(path):
+        c = [v.strip() for v in line.split(",")]
+        if len(c) < 9:
+            continue
+        try:
+            sm.append(float(c[1]))
+            smax = float(c[2])
+        except ValueError:
+            continue
+        for nm, v in zip(names, c[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(nm)
+    # "under load": the upper half of the samples (the sampler also sees idle gaps around the region)
+    sm.sort()
+    load = sm[len(sm) // 2:] if sm else []
+    return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, len(os.sched_getaffinity(0))
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/torch_port.py) -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, batch):
+    from oracle import torch_port as TP
+    from train.unet import TemporalUNetDualView
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).state_dict()
+    p = TP.params_from_state_dict(sd, torch.float32)
+    opt = torch.optim.AdamW([v for v in p.values() if v.requires_grad], lr=1e-3, weight_decay=1e-4)
+    x, y = make_batch(batch, args.seq_len, args.size, 1234)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out, _ = TP.temporal_unet(p, x, None, training=True)
+        loss = ((torch.stack(out, dim=1) - y) ** 2).mean()
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: 4 sequences per step (2 when many steps are asked for) so the run ends in minutes
+    batch = 4 if args.steps + args.warmup <= 10 else 2
+    value, dt, cores = cpu_reference_run(args, args.steps, args.warmup, batch)
+    cpu_model, _ = host_info()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch_per_step=batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model,
+                         "sample": f"{batch} sequence(s) per step (T={args.seq_len}, {args.size}x{args.size}, base_ch "
+                                   f"{args.base_ch} + skip LSTMs), fwd+bwd+AdamW, fp32, torch {torch.__version__} CPU "
+                                   f"(oneDNN), {args.steps} timed steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch_per_step=None):
+    return {
+        "workload": f"Moving-MNIST-shaped UNet-ConvLSTM {args.size}x{args.size}, T={args.seq_len}, "
+                    f"batch {args.batch} per GPU, base_ch {args.base_ch} + skip ConvLSTMs (BASELINE.json configs[1])",
+        "batch_per_gpu": args.batch if batch_per_step is None else batch_per_step, "seq_len": args.seq_len,
+        "image": args.size, "base_ch": args.base_ch, "use_skip_lstm": True, "precision": args.precision,
+        "step": "forward + backward + AdamW(fused) update; gradient all-reduce overlapped when N > 1",
+        "parallelism": f"dp{args.gpus}",
+        "l2": "per-step working set (tens of GB of activations, 168 MB of inputs) far exceeds the 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch.distributed as dist
+    import unet_convlstm_b200 as pkg
+    from train.unet import TemporalUNetDualView
+    from unet_convlstm_b200 import _lib, ops
+    from unet_convlstm_b200.dist import GradReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    pkg.set_precision(args.precision)
+    _lib.lib()  # fail loudly if the CUDA library is missing
+
+    torch.manual_seed(0)  # identical replicas
+    model = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).to(dev)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    reducer = GradReducer(model.parameters()) if world > 1 else None
+
+    x_host, y_host = make_batch(args.batch, args.seq_len, args.size, 1234 + rank)
+    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step(x, y, with_opt=True):
+        opt.zero_grad(set_to_none=True)
+        out, _ = model(x)
+        loss = ((torch.stack(out, dim=1) - y) ** 2).mean()
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        if with_opt:
+            opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+
+    clk_path = os.path.join(ROOT, "gpurun_out", f"bench_clocks_r{rank}.csv")
+    os.makedirs(os.path.dirname(clk_path), exist_ok=True)
+    proc, f = clocks_sampler_start(local, clk_path) if rank == 0 else (None, None)
+
+    # ---- timed region 1: inputs resident in HBM -------------------------------------------------
+    ops.CELL_TIMER = []
+    calls0 = _lib.kernel_launches()
+    ms_step = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = _lib.kernel_launches() - calls0
+    cell_events, ops.CELL_TIMER = ops.CELL_TIMER, None
+    torch.cuda.synchronize()
+    cell_ms = [a.elapsed_time(b) for a, b, _ in cell_events]
+    cell_flops = [fl for _, _, fl in cell_events]
+
+    # ---- timed region 2: end to end through the module API, batch in pinned host memory ----------
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        y = y_host.to(dev, non_blocking=True)
+        return step(x, y).item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- fwd+bwd only (no optimizer), for the record --------------------------------------------
+    ms_fb = timed(lambda: step(x_dev, y_dev, with_opt=False), max(1, args.steps // 2))
+    clocks = clocks_summary(proc, f, clk_path) if rank == 0 else None
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained")
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+        if peak_tf is None:
+            peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+        full = [(m, fl) for m, fl in zip(cell_ms, cell_flops) if fl == max(cell_flops)] if cell_flops else []
+        ach = (sum(fl for _, fl in full) / (sum(m for m, _ in full) * 1e-3) / 1e12) if full else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("cell_fwd_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": world * args.batch / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": world * args.batch / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4, "d2h_bytes_per_step": 4},
+            "fwd_bwd_only": {"value": world * args.batch / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "conv_tc_kernel<256, EPI_LSTM> (fused ConvLSTM gate conv + cell update, forward)",
+                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (ach / peak_tf) if ach else None, "traffic": traffic, "peak_source": peak_src,
+                         "launches_timed": len(full),
+                         "avg_launch_ms": (sum(m for m, _ in full) / len(full)) if full else None,
+                         "flops_per_launch": max(cell_flops) if cell_flops else None,
+                         "share_of_step": (sum(cell_ms) / args.steps / ms_step) if cell_ms else None},
+            "clocks": clocks,
+            "peak_mem_gb": peak_mem / 2 ** 30,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, cores = cpu_reference_run(args, 1, 0, args.cpu_sample)
+            cpu_model, _ = host_info()
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model,
+                "sample": f"{args.cpu_sample} sequence(s), 1 fwd+bwd+AdamW step of the same model and shapes "
+                          f"(T={args.seq_len}, {args.size}x{args.size}), fp32, torch {torch.__version__} CPU "
+                          f"(oneDNN) = the reference's own ATen operators (oracle/torch_port.py), {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU and step")
+    ap.add_argument("--seq-len", type=int, default=20)
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--base-ch", type=int, default=64)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=2, help="sequences in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

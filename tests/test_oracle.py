@@ -150,3 +150,51 @@ def test_model_matches_reference(golden_dir, name):
 
 def test_fixture_set_is_complete(golden_dir):
     assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 10
+
+
+# --------------------------------------------------------------------------------------------
+# oracle/torch_port.py (the CPU baseline of bench.py) against the same fixtures
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["model_b4_skip.npz", "model_b2_noskip_l2.npz", "model_b4_skip_64.npz"])
+def test_torch_port_model_matches_reference(golden_dir, name):
+    import torch
+    from oracle import torch_port as TP
+    z = np.load(os.path.join(golden_dir, name))
+    base_ch, skip, L, B, T, H, W = z["meta"]
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p.")}
+    p = TP.params_from_state_dict(sd, torch.float64)
+    x = torch.from_numpy(z["x"]).double().requires_grad_(True)
+    out, st = TP.temporal_unet(p, x, None, training=True)
+    y = torch.stack(out, dim=1)
+    assert rel(y.detach().numpy(), z["y_train"]) < 1e-9
+    (y * torch.from_numpy(z["dy"]).double()).sum().backward()
+    assert rel(x.grad.numpy(), z["dx"]) < 1e-7
+    for k in z.files:
+        if k.startswith("g."):
+            ref = z[k].astype(np.float64)
+            g = p[k[2:]].grad.numpy()
+            if np.abs(ref).max() < 1e-7 * max(1.0, np.abs(z["dy"]).max()):
+                assert np.abs(g).max() < 1e-6, k
+            else:
+                assert rel(g, ref) < 5e-6, k
+        if k.startswith("after."):
+            assert rel(p[k[6:]].double().numpy(), z[k].astype(np.float64)) < 1e-10, k
+    for l in range(L):
+        assert rel(st[l][0].detach().numpy(), z[f"hT{l}"]) < 1e-9
+    with torch.no_grad():
+        oe, _ = TP.temporal_unet(p, x.detach(), None, training=False)
+    assert rel(torch.stack(oe, dim=1).numpy(), z["y_eval"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["convlstm_c6_12_l2_state.npz", "convlstm_c16_l1_state.npz"])
+def test_torch_port_convlstm_matches_reference(golden_dir, name):
+    import torch
+    from oracle import torch_port as TP
+    z = np.load(os.path.join(golden_dir, name))
+    cin, ch, L, B, T, H, W, with_state = z["meta"]
+    p = {"m." + k[2:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("p.")}
+    state = [(torch.from_numpy(z[f"h0{l}"]).double(), torch.from_numpy(z[f"c0{l}"]).double()) for l in range(L)]
+    out, ns = TP.convlstm(p, "m", [torch.from_numpy(a).double() for a in z["x"]], state)
+    assert rel(torch.stack(out).numpy(), z["out"]) < 1e-10
+    for l in range(L):
+        assert rel(ns[l][1].numpy(), z[f"cT{l}"]) < 1e-10

@@ -27,9 +27,16 @@ def errs(a, b):
             np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30), np.abs(b).max())
 
 
+FLOORS = None  # (npz, prefix) of the fixture being reported
+
+
 def show(name, a, b):
     m, l2, mag = errs(a, b)
-    print(f"    {name:44s} max-rel {m:9.2e}  l2-rel {l2:9.2e}  |ref|max {mag:9.2e}")
+    fl = ""
+    if FLOORS is not None and (FLOORS[1] + name) in FLOORS[0].files:
+        f = FLOORS[0][FLOORS[1] + name]
+        fl = f"  floor max {f[0]:8.2e} l2 {f[1]:8.2e}  ratio {l2 / max(f[1], 1e-30):6.1f}"
+    print(f"    {name:44s} max-rel {m:9.2e}  l2-rel {l2:9.2e}  |ref|max {mag:9.2e}{fl}")
 
 
 def _np(t):
@@ -62,6 +69,8 @@ def run(mode):
     for path in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         name = os.path.basename(path)
         z = np.load(path)
+        global FLOORS
+        FLOORS = (z, "e32." if mode == "fp32" else "e16.")
         print(f"  -- {name}")
         if name.startswith("convlstm"):
             cin, ch, L, B, T, H, W, ws = [int(v) for v in z["meta"]]

@@ -48,6 +48,21 @@ def parse_header(path: str = HEADER):
 _lib = None
 _protos = None
 
+# C-ABI calls made so far, by entry point (bench.py turns these into its `gpu_launches` claim)
+CALLS: dict = {}
+# device kernels launched per call of each entry point (memsets are not counted)
+KERNELS_PER_CALL = {
+    "b200_conv_tc_fwd": 1, "b200_convlstm_cell_fwd_tc": 1, "b200_wgrad_tc": 1, "b200_conv_simt_fwd": 1,
+    "b200_wgrad_simt": 1, "b200_bn_stats": 1, "b200_bn_finalize": 1, "b200_bn_relu_apply": 1,
+    "b200_bn_relu_bwd_reduce": 1, "b200_bn_bwd_finalize": 1, "b200_bn_relu_bwd_apply": 1,
+    "b200_maxpool2_fwd": 1, "b200_maxpool2_bwd": 1, "b200_lstm_gates_fwd": 1, "b200_lstm_gates_bwd": 1,
+    "b200_colsum": 2, "b200_outconv_fwd": 1, "b200_outconv_bwd": 5, "b200_shuffle2x2": 1, "b200_strided_copy": 1,
+}
+
+
+def kernel_launches() -> int:
+    return sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in CALLS.items())
+
 
 def lib():
     global _lib, _protos
@@ -73,6 +88,7 @@ def last_error() -> str:
 def call(name: str, *args):
     """Calls an int-returning entry point and raises on a non-zero status."""
     rc = getattr(lib(), name)(*args)
+    CALLS[name] = CALLS.get(name, 0) + 1
     if rc != 0:
         raise RuntimeError(f"{name} failed: rc={rc}: {last_error()}")
 

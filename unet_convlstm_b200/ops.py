@@ -349,12 +349,26 @@ def lstm_tc_ok(x_t, Ch) -> bool:
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
 
+# bench.py sets this to a list to time every fused cell launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, algorithmic_flops)
+CELL_TIMER = None
+
+
 def lstm_cell_fwd_fused(x_t, h_prev, c_prev, wp_il, bias_il, c_next, h_next, gates, ksize):
     """One fused cell step on the tensor cores (gate conv + gate math + state update)."""
     B, H, W, Cin = x_t.shape
     Ch = c_next.shape[-1]
+    timer = CELL_TIMER
+    if timer is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("b200_convlstm_cell_fwd_tc", _p(x_t), Cin, _p(h_prev), Ch, B, H, W, _p(wp_il), _p(bias_il),
               _p(c_prev), _p(c_next), _p(h_next), _p(gates), ksize, _st())
+    if timer is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        kin = Cin + (Ch if h_prev is not None else 0)
+        timer.append((e0, e1, 2.0 * B * H * W * ksize * ksize * kin * 4 * Ch))
 
 
 def lstm_cell_fwd_unfused(x_t, h_prev, c_prev, wp, bias, c_next, h_next, gates, ksize, zbuf):
