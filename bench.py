@@ -246,6 +246,13 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
+    if args.profile_steps:
+        # for `ncu`: one warm-up step (packs weights, sizes the caching allocator) + N plain steps, no timing
+        for _ in range(1 + args.profile_steps):
+            step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        return
+
     for _ in range(args.warmup):
         step(x_dev, y_dev)
 
@@ -339,6 +346,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=2, help="sequences in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=0, help="run 1 warm-up + N untimed steps and exit (for ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
