@@ -87,8 +87,11 @@ int b200_bn_relu_apply(const void* x, const float* scale, const float* shift, vo
 int b200_bn_relu_bwd_reduce(const void* x, const void* dy, const float* mean, const float* rstd,
                             const float* scale, const float* shift, int T, long long P, int C, int tstride,
                             int dtype_fp32, double* sum_g, double* sum_gx, void* stream);
+/* also yields the gradient of the preceding conv's bias, dconv_bias = sum_pixels dx (may be NULL): it is
+ * identically zero in training mode and scale*sum_g in eval mode (scale: [C], the eval-mode scale) */
 int b200_bn_bwd_finalize(const double* sum_g, const double* sum_gx, int T, long long n, int C, int training,
-                         float* coef1, float* coef2, float* dgamma, float* dbeta, int accumulate, void* stream);
+                         const float* scale, float* coef1, float* coef2, float* dgamma, float* dbeta,
+                         float* dconv_bias, int accumulate, void* stream);
 /* dx = scale*(g - coef1 - xhat*coef2) */
 int b200_bn_relu_bwd_apply(const void* x, const void* dy, const float* mean, const float* rstd,
                            const float* scale, const float* shift, const float* coef1, const float* coef2,

@@ -346,6 +346,7 @@ def test_conv_tc_vs_simt(T, B, H, W, C0, C1, N, ks):
 @pytest.mark.parametrize("T,B,H,W,Nz,C0,C1,ks", [(1, 2, 8, 8, 128, 64, 0, 3), (2, 4, 4, 4, 256, 128, 128, 3),
                                                  (3, 2, 16, 16, 64, 64, 0, 3), (2, 2, 32, 32, 128, 32, 96, 3),
                                                  (1, 1, 12, 16, 64, 16, 0, 3), (2, 2, 8, 128, 320, 320, 0, 1),
+                                                 (1, 2, 8, 8, 320, 64, 0, 3), (2, 2, 16, 16, 128, 64, 64, 3),
                                                  (4, 8, 64, 64, 64, 64, 0, 3)])
 def test_wgrad_tc_vs_simt(T, B, H, W, Nz, C0, C1, ks):
     from unet_convlstm_b200 import _lib, ops

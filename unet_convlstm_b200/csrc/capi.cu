@@ -170,12 +170,12 @@ extern "C" int b200_bn_relu_bwd_reduce(const void* x, const void* dy, const floa
 }
 
 extern "C" int b200_bn_bwd_finalize(const double* sum_g, const double* sum_gx, int T, long long n, int C,
-                                    int training, float* coef1, float* coef2, float* dgamma, float* dbeta,
-                                    int accumulate, void* stream) {
-    B200_REQUIRE(sum_g && sum_gx && coef1 && coef2 && dgamma && dbeta && T > 0 && n > 0 && C > 0,
+                                    int training, const float* scale, float* coef1, float* coef2, float* dgamma,
+                                    float* dbeta, float* dconv_bias, int accumulate, void* stream) {
+    B200_REQUIRE(sum_g && sum_gx && scale && coef1 && coef2 && dgamma && dbeta && T > 0 && n > 0 && C > 0,
                  "b200_bn_bwd_finalize");
-    return launch_bn_bwd_finalize(sum_g, sum_gx, T, n, C, training, coef1, coef2, dgamma, dbeta, accumulate,
-                                  static_cast<cudaStream_t>(stream));
+    return launch_bn_bwd_finalize(sum_g, sum_gx, T, n, C, training, scale, coef1, coef2, dgamma, dbeta, dconv_bias,
+                                  accumulate, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_bn_relu_bwd_apply(const void* x, const void* dy, const float* mean, const float* rstd,

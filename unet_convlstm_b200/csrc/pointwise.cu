@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const Op op, const Reduc
 #pragma unroll
     for (int j = 0; j < V; ++j) a0[j] = a1[j] = Acc(0);
     if (active) {
-#pragma unroll 2
-        for (long long p = p_begin + r; p < p_end; p += g.rows_per_iter) op.template accum<T, V, Acc>(t, p, c, a0, a1);
+        typename Op::template State<V> st;  // per-thread coefficients, loaded once
+        op.template init<V>(t, c, st);
+#pragma unroll 4
+        for (long long p = p_begin + r; p < p_end; p += g.rows_per_iter)
+            op.template accum<T, V, Acc>(st, t, p, c, a0, a1);
     }
     // combine the rows_per_iter partial sums of each channel
     constexpr int HV = V > 4 ? 4 : V;
@@ -182,12 +185,20 @@ static int launch_colreduce(const Op& op, int T_, long long P, int C, int V, dou
 }
 
 // ---- BatchNorm statistics: sum x, sum x^2 (nn.BatchNorm2d training forward, unet.py:70-71) ----
-struct StatsOp {
+struct NoState {
+    template <int V>
+    struct State {};
+    template <int V>
+    __device__ __forceinline__ void init(int, int, State<V>&) const {}
+};
+
+struct StatsOp : NoState {
     const void* x;
     long long P;
     int C;
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(int t, long long p, int c, Acc (&a0)[V], Acc (&a1)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>&, int t, long long p, int c, Acc (&a0)[V],
+                                          Acc (&a1)[V]) const {
         float f[V];
         ldv<T, V>(static_cast<const T*>(x) + (static_cast<long long>(t) * P + p) * C + c, f);
 #pragma unroll
@@ -202,17 +213,18 @@ int launch_bn_stats(const void* x, int T_, long long P, int C, int dtype_fp32, d
                     cudaStream_t stream) {
     B200_CUDA_CHECK(cudaMemsetAsync(sum, 0, sizeof(double) * T_ * C, stream));
     B200_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, sizeof(double) * T_ * C, stream));
-    StatsOp op{x, P, C};
+    StatsOp op;
+    op.x = x; op.P = P; op.C = C;
     if (dtype_fp32) return launch_colreduce<float>(op, T_, P, C, pick_vec<float>(C, {x}), sum, sumsq, stream);
     return launch_colreduce<__nv_bfloat16>(op, T_, P, C, pick_vec<__nv_bfloat16>(C, {x}), sum, sumsq, stream);
 }
 
 // ---- plain column sum (bias gradients) ----
-struct ColsumOp {
+struct ColsumOp : NoState {
     const void* x;
     int C;
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(int, long long p, int c, Acc (&a0)[V], Acc (&)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>&, int, long long p, int c, Acc (&a0)[V], Acc (&)[V]) const {
         float f[V];
         ldv<T, V>(static_cast<const T*>(x) + p * C + c, f);
 #pragma unroll
@@ -222,7 +234,8 @@ struct ColsumOp {
 
 int launch_colsum(const void* x, long long rows, int C, int dtype_fp32, double* out, cudaStream_t stream) {
     B200_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * C, stream));
-    ColsumOp op{x, C};
+    ColsumOp op;
+    op.x = x; op.C = C;
     if (dtype_fp32) return launch_colreduce<float>(op, 1, rows, C, pick_vec<float>(C, {x}), out, nullptr, stream);
     return launch_colreduce<__nv_bfloat16>(op, 1, rows, C, pick_vec<__nv_bfloat16>(C, {x}), out, nullptr, stream);
 }
@@ -238,18 +251,33 @@ struct BnBwdReduceOp {
     long long P;
     int C;
     int tstride;  // C in training mode, 0 in eval mode (one set of statistics for every t)
+    template <int V>
+    struct State {
+        float sc[V], sh[V], mu[V], rs[V];
+    };
+    template <int V>
+    __device__ __forceinline__ void init(int t, int c, State<V>& st) const {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int i = t * tstride + c + j;
+            st.sc[j] = __ldg(scale + i);
+            st.sh[j] = __ldg(shift + i);
+            st.mu[j] = __ldg(mean + i);
+            st.rs[j] = __ldg(rstd + i);
+        }
+    }
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(int t, long long p, int c, Acc (&a0)[V], Acc (&a1)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>& st, int t, long long p, int c, Acc (&a0)[V],
+                                          Acc (&a1)[V]) const {
         float fx[V], fd[V];
         const long long off = (static_cast<long long>(t) * P + p) * C + c;
         ldv<T, V>(static_cast<const T*>(x) + off, fx);
         ldv<T, V>(static_cast<const T*>(dy) + off, fd);
-        const int sc = t * tstride + c;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            const float yv = fmaf(fx[j], __ldg(scale + sc + j), __ldg(shift + sc + j));
+            const float yv = fmaf(fx[j], st.sc[j], st.sh[j]);
             const float gq = yv > 0.f ? fd[j] : 0.f;
-            const float xh = (fx[j] - __ldg(mean + sc + j)) * __ldg(rstd + sc + j);
+            const float xh = (fx[j] - st.mu[j]) * st.rs[j];
             a0[j] += Acc(gq);
             a1[j] += Acc(gq) * Acc(xh);
         }
@@ -268,12 +296,12 @@ int launch_bn_relu_bwd_reduce(const void* x, const void* dy, const float* mean, 
 }
 
 // ---- 1x1 output conv weight gradient: dw[o][c] = sum_p dy[p][o] * x[p][c] (OutConv, unet.py:104) ----
-struct OutconvWgradOp {
+struct OutconvWgradOp : NoState {
     const void* x;
     const float* dy;  // [P][O] fp32
     int C, O, o;
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(int, long long p, int c, Acc (&a0)[V], Acc (&)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>&, int, long long p, int c, Acc (&a0)[V], Acc (&)[V]) const {
         float f[V];
         ldv<T, V>(static_cast<const T*>(x) + p * C + c, f);
         const float d = __ldg(dy + p * O + o);
@@ -285,7 +313,8 @@ struct OutconvWgradOp {
 int launch_outconv_wgrad(const void* x, const float* dy, long long P, int C, int O, int o, int dtype_fp32,
                          double* out, cudaStream_t stream) {
     B200_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * C, stream));
-    OutconvWgradOp op{x, dy, C, O, o};
+    OutconvWgradOp op;
+    op.x = x; op.dy = dy; op.C = C; op.O = O; op.o = o;
     if (dtype_fp32) return launch_colreduce<float>(op, 1, P, C, pick_vec<float>(C, {x}), out, nullptr, stream);
     return launch_colreduce<__nv_bfloat16>(op, 1, P, C, pick_vec<__nv_bfloat16>(C, {x}), out, nullptr, stream);
 }
@@ -344,10 +373,13 @@ int launch_bn_finalize(const double* sum, const double* sumsq, int T_, long long
 }
 
 // coef1 = sum_g / n, coef2 = sum_gx / n (zero in eval mode); dgamma += sum_t sum_gx, dbeta += sum_t sum_g
+// dconv_bias = sum over pixels of dz = scale * (sum_g - n*coef1 - coef2 * sum xhat): identically zero in
+// training mode (sum xhat = 0, n*coef1 = sum_g); scale * sum_g with running statistics (eval mode).
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, int T_,
-                                       long long n, int C, int training, float* __restrict__ coef1,
-                                       float* __restrict__ coef2, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate) {
+                                       long long n, int C, int training, const float* __restrict__ scale,
+                                       float* __restrict__ coef1, float* __restrict__ coef2,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ dconv_bias, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double dg = 0, db = 0;
@@ -358,20 +390,23 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
         coef1[t * C + c] = training ? static_cast<float>(sg / n) : 0.f;
         coef2[t * C + c] = training ? static_cast<float>(sgx / n) : 0.f;
     }
+    const float dcb = training ? 0.f : static_cast<float>(scale[c] * db);
     if (accumulate) {
         dgamma[c] += static_cast<float>(dg);
         dbeta[c] += static_cast<float>(db);
+        if (dconv_bias) dconv_bias[c] += dcb;
     } else {
         dgamma[c] = static_cast<float>(dg);
         dbeta[c] = static_cast<float>(db);
+        if (dconv_bias) dconv_bias[c] = dcb;
     }
 }
 
 int launch_bn_bwd_finalize(const double* sum_g, const double* sum_gx, int T_, long long n, int C, int training,
-                           float* coef1, float* coef2, float* dgamma, float* dbeta, int accumulate,
-                           cudaStream_t stream) {
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum_g, sum_gx, T_, n, C, training, coef1, coef2,
-                                                                dgamma, dbeta, accumulate);
+                           const float* scale, float* coef1, float* coef2, float* dgamma, float* dbeta,
+                           float* dconv_bias, int accumulate, cudaStream_t stream) {
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum_g, sum_gx, T_, n, C, training, scale, coef1,
+                                                                coef2, dgamma, dbeta, dconv_bias, accumulate);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200_OK;
 }
@@ -392,44 +427,77 @@ int launch_cast_double(const double* src, float* dst, int n, int accumulate, cud
 // ------------------------------------------------------------------------------------------------
 // element-wise kernels over [T][P][C]
 // ------------------------------------------------------------------------------------------------
+// Row-loop geometry shared by the BatchNorm apply kernels: like colreduce, a thread owns a fixed vector
+// of V channels of one timestep, so the per-(t, channel) coefficients are loaded ONCE into registers
+// and the loop over pixels only touches the activations (an earlier version re-read six coefficient
+// arrays per element and was L1-bound at 56 % of HBM peak, profiles/r01_ncu_bn_relu_bwd_apply.txt).
+static ReduceGeom rowloop_geom(int T_, long long P, int C, int V, dim3* grid) {
+    ReduceGeom g;
+    g.T = T_;
+    g.P = P;
+    g.C = C;
+    const int CV = C / V;
+    g.cvb = CV < 256 ? CV : 256;
+    g.rows_per_iter = 256 / g.cvb;
+    const unsigned gy = (CV + g.cvb - 1) / g.cvb;
+    long long want_x = (16LL * num_sms() + (long long)gy * T_ - 1) / ((long long)gy * T_);
+    long long max_x = (P + 8LL * g.rows_per_iter - 1) / (8LL * g.rows_per_iter);
+    if (want_x > max_x) want_x = max_x;
+    if (want_x < 1) want_x = 1;
+    g.rows_per_block = (P + want_x - 1) / want_x;
+    *grid = dim3(static_cast<unsigned>((P + g.rows_per_block - 1) / g.rows_per_block), gy, T_);
+    return g;
+}
+
 // y = relu(x * scale[t][c] + shift[t][c])   (BatchNorm2d + ReLU, unet.py:70-71)
 template <typename T, int V>
 __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, T* __restrict__ y,
-                                                            long long nvec, long long vec_per_t, int CV,
-                                                            int tstride, int relu) {
-    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec;
-         v += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int t = static_cast<int>(v / vec_per_t);
-        const int c = static_cast<int>(v % CV) * V;
+                                                            const ReduceGeom g, int tstride, int relu) {
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;
+    const int cv = tid - r * g.cvb;
+    const int c = (blockIdx.y * g.cvb + cv) * V;
+    const int t = blockIdx.z;
+    if (r >= g.rows_per_iter || c >= g.C) return;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = __ldg(scale + t * tstride + c + j);
+        sh[j] = __ldg(shift + t * tstride + c + j);
+    }
+    const long long p_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long p_end = p_begin + g.rows_per_block;
+    if (p_end > g.P) p_end = g.P;
+    const long long base = static_cast<long long>(t) * g.P;
+#pragma unroll 4
+    for (long long p = p_begin + r; p < p_end; p += g.rows_per_iter) {
+        const long long off = (base + p) * g.C + c;
         float f[V];
-        ldv<T, V>(x + v * V, f);
-        const int sc = t * tstride + c;
+        ldv<T, V>(x + off, f);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            f[j] = fmaf(f[j], __ldg(scale + sc + j), __ldg(shift + sc + j));
+            f[j] = fmaf(f[j], sc[j], sh[j]);
             if (relu) f[j] = fmaxf(f[j], 0.f);
         }
-        stv<T, V>(y + v * V, f);
+        stv<T, V>(y + off, f);
     }
 }
 
 int launch_bn_relu_apply(const void* x, const float* scale, const float* shift, void* y, int T_, long long P, int C,
                          int tstride, int relu, int dtype_fp32, cudaStream_t stream) {
-    const long long total = static_cast<long long>(T_) * P * C;
-    auto go = [&](auto tag, int V) -> int {
+    auto go = [&](auto tag, int V) {
         using T = decltype(tag);
-        const long long nvec = total / V;
-        const unsigned grid = grid_for(nvec, 256 * 4, num_sms() * 16);
+        dim3 grid;
+        const ReduceGeom g = rowloop_geom(T_, P, C, V, &grid);
         const T* xs = static_cast<const T*>(x);
         T* ys = static_cast<T*>(y);
         if (V == 1)
-            bn_relu_apply_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, nvec, P * C, C, tstride, relu);
+            bn_relu_apply_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, g, tstride, relu);
         else if constexpr (std::is_same<T, float>::value)
-            bn_relu_apply_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, nvec, P * C / 4, C / 4, tstride, relu);
+            bn_relu_apply_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, g, tstride, relu);
         else
-            bn_relu_apply_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, nvec, P * C / 8, C / 8, tstride, relu);
-        return 0;
+            bn_relu_apply_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, g, tstride, relu);
     };
     if (dtype_fp32)
         go(float(), pick_vec<float>(C, {x, y}));
@@ -439,52 +507,65 @@ int launch_bn_relu_apply(const void* x, const float* scale, const float* shift, 
     return B200_OK;
 }
 
-// dx = scale * (g - coef1 - xhat * coef2),  g = dy * [x*scale+shift > 0]
+// dx = scale * (g - coef1 - xhat * coef2),  g = dy * [x*scale+shift > 0],  xhat = (x - mean) * rstd
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                          const float* __restrict__ rstd, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ coef1,
-                         const float* __restrict__ coef2, T* __restrict__ dx, long long nvec, long long vec_per_t,
-                         int CV, int C, int tstride) {
-    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec;
-         v += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int t = static_cast<int>(v / vec_per_t);
-        const int c = static_cast<int>(v % CV) * V;
+                         const float* __restrict__ coef2, T* __restrict__ dx, const ReduceGeom g, int tstride) {
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;
+    const int cv = tid - r * g.cvb;
+    const int c = (blockIdx.y * g.cvb + cv) * V;
+    const int t = blockIdx.z;
+    if (r >= g.rows_per_iter || c >= g.C) return;
+    float sc[V], sh[V], mu[V], rc2[V], c1[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int ps = t * tstride + c + j, pc = t * g.C + c + j;
+        sc[j] = __ldg(scale + ps);
+        sh[j] = __ldg(shift + ps);
+        mu[j] = __ldg(mean + ps);
+        rc2[j] = __ldg(rstd + ps) * __ldg(coef2 + pc);
+        c1[j] = __ldg(coef1 + pc);
+    }
+    const long long p_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long p_end = p_begin + g.rows_per_block;
+    if (p_end > g.P) p_end = g.P;
+    const long long base = static_cast<long long>(t) * g.P;
+#pragma unroll 4
+    for (long long p = p_begin + r; p < p_end; p += g.rows_per_iter) {
+        const long long off = (base + p) * g.C + c;
         float fx[V], fd[V];
-        ldv<T, V>(x + v * V, fx);
-        ldv<T, V>(dy + v * V, fd);
-        const int sc = t * tstride + c;
-        const int cc = t * C + c;
+        ldv<T, V>(x + off, fx);
+        ldv<T, V>(dy + off, fd);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            const float s = __ldg(scale + sc + j);
-            const float yv = fmaf(fx[j], s, __ldg(shift + sc + j));
+            const float yv = fmaf(fx[j], sc[j], sh[j]);
             const float gq = yv > 0.f ? fd[j] : 0.f;
-            const float xh = (fx[j] - __ldg(mean + sc + j)) * __ldg(rstd + sc + j);
-            fd[j] = s * (gq - __ldg(coef1 + cc + j) - xh * __ldg(coef2 + cc + j));
+            fd[j] = sc[j] * (gq - c1[j] - (fx[j] - mu[j]) * rc2[j]);
         }
-        stv<T, V>(dx + v * V, fd);
+        stv<T, V>(dx + off, fd);
     }
 }
 
 int launch_bn_relu_bwd_apply(const void* x, const void* dy, const float* mean, const float* rstd, const float* scale,
                              const float* shift, const float* coef1, const float* coef2, void* dx, int T_,
                              long long P, int C, int tstride, int dtype_fp32, cudaStream_t stream) {
-    const long long total = static_cast<long long>(T_) * P * C;
     auto go = [&](auto tag, int V) {
         using T = decltype(tag);
-        const long long nvec = total / V;
-        const unsigned grid = grid_for(nvec, 256 * 2, num_sms() * 16);
+        dim3 grid;
+        const ReduceGeom g = rowloop_geom(T_, P, C, V, &grid);
         const T* xs = static_cast<const T*>(x);
         const T* ds = static_cast<const T*>(dy);
         T* os = static_cast<T*>(dx);
         if (V == 1)
-            bn_relu_bwd_apply_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, ds, mean, rstd, scale, shift, coef1, coef2, os, nvec, P * C, C, C, tstride);
+            bn_relu_bwd_apply_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, ds, mean, rstd, scale, shift, coef1, coef2, os, g, tstride);
         else if constexpr (std::is_same<T, float>::value)
-            bn_relu_bwd_apply_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, ds, mean, rstd, scale, shift, coef1, coef2, os, nvec, P * C / 4, C / 4, C, tstride);
+            bn_relu_bwd_apply_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, ds, mean, rstd, scale, shift, coef1, coef2, os, g, tstride);
         else
-            bn_relu_bwd_apply_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, ds, mean, rstd, scale, shift, coef1, coef2, os, nvec, P * C / 8, C / 8, C, tstride);
+            bn_relu_bwd_apply_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, ds, mean, rstd, scale, shift, coef1, coef2, os, g, tstride);
     };
     if (dtype_fp32)
         go(float(), pick_vec<float>(C, {x, dy, dx}));

@@ -17,8 +17,8 @@ int launch_bn_finalize(const double* sum, const double* sumsq, int T, long long 
                        const float* beta, float* running_mean, float* running_var, float eps, float momentum,
                        int training, float* mean, float* rstd, float* scale, float* shift, cudaStream_t stream);
 int launch_bn_bwd_finalize(const double* sum_g, const double* sum_gx, int T, long long n, int C, int training,
-                           float* coef1, float* coef2, float* dgamma, float* dbeta, int accumulate,
-                           cudaStream_t stream);
+                           const float* scale, float* coef1, float* coef2, float* dgamma, float* dbeta,
+                           float* dconv_bias, int accumulate, cudaStream_t stream);
 int launch_cast_double(const double* src, float* dst, int n, int accumulate, cudaStream_t stream);
 int launch_bn_relu_apply(const void* x, const float* scale, const float* shift, void* y, int T, long long P, int C,
                          int tstride, int relu, int dtype_fp32, cudaStream_t stream);

@@ -15,6 +15,11 @@
 // with SBO = 8 pixel rows and LBO = one whole box (next channel chunk).  The tap shift and the
 // zero padding are the TMA coordinates / out-of-bounds fill of the source box, as in conv_tc.cu.
 //
+// Stacked mode (source with 16/32/64 channels, the full-resolution UNet layers): an M tile of
+// 128 dz channels would be half empty and every tap would re-read dz, so the roles are swapped:
+// A = G = 128/Csrc tap-shifted source boxes stacked along M (rows = (tap, source channel)),
+// B = dz channels (N).  One unit then covers G taps with one dz load per K block.
+//
 // Work units = (reduction split s) x (tap, M tile, N tile); partial sums of different splits
 // are combined with vectorised fp32 reductions (red.global.add.v4.f32) into the caller's
 // zero-initialised buffer.  Warp roles are those of conv_tc.cu.
@@ -37,6 +42,8 @@ struct WgradParams {
     int num_rblocks; // T * tiles_w * tiles_h * tiles_b
     int rb_per_split, splits;
     int num_m_tiles, num_n_tiles, out_tiles;
+    int stacked;     // 1: A = tap-stacked source boxes (G taps x Csrc = 128 rows), B = dz; see below
+    int G;           // taps per unit in stacked mode
     float* dw;       // [taps][Nz][ldk]
     long long ldk;
     int koff;
@@ -57,6 +64,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
                  "f"(d)
                  : "memory");
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
 template <int BLOCK_N>
@@ -118,7 +129,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         tap = ot / p.num_m_tiles;
         m0 = mt * WG_BLOCK_M;
         n0 = nt * BLOCK_N;
-        ncols = min(BLOCK_N, p.Csrc - n0);
+        // stacked mode: "tap" is the tap group, N runs over dz channels
+        ncols = min(BLOCK_N, (p.stacked ? p.Nz : p.Csrc) - n0);
     };
 
     if (warp == 0) {
@@ -145,12 +157,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                     mbar_arrive_expect_tx(full_bar(stage), boxesA * boxA_bytes + boxesB * boxB_bytes);
                     const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-                    for (int i = 0; i < boxesA; ++i)
-                        tma_load_5d(a_dst + i * boxA_bytes, &tm_dz, full_bar(stage), m0 + i * p.cwA, w0,
-                                    h0, b0, t);
-                    for (int i = 0; i < boxesB; ++i)
-                        tma_load_5d(b_dst + i * boxB_bytes, &tm_src, full_bar(stage), n0 + i * p.cwB,
-                                    w0 + kx - p.pad, h0 + ky - p.pad, b0, t);
+                    if (p.stacked) {
+                        const int taps = p.ksize * p.ksize;
+                        for (int i = 0; i < boxesA; ++i) {
+                            // taps beyond the filter repeat the last one; their rows are never stored
+                            const int tp = min(tap * p.G + i, taps - 1);
+                            const int sy = tp / p.ksize, sx = tp - sy * p.ksize;
+                            tma_load_5d(a_dst + i * boxA_bytes, &tm_src, full_bar(stage), 0, w0 + sx - p.pad,
+                                        h0 + sy - p.pad, b0, t);
+                        }
+                        for (int i = 0; i < boxesB; ++i)
+                            tma_load_5d(b_dst + i * boxB_bytes, &tm_dz, full_bar(stage), n0 + i * p.cwB, w0, h0,
+                                        b0, t);
+                    } else {
+                        for (int i = 0; i < boxesA; ++i)
+                            tma_load_5d(a_dst + i * boxA_bytes, &tm_dz, full_bar(stage), m0 + i * p.cwA, w0,
+                                        h0, b0, t);
+                        for (int i = 0; i < boxesB; ++i)
+                            tma_load_5d(b_dst + i * boxB_bytes, &tm_src, full_bar(stage), n0 + i * p.cwB,
+                                        w0 + kx - p.pad, h0 + ky - p.pad, b0, t);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -213,8 +239,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             int split, tap, m0, n0, ncols;
             decode(unit, split, tap, m0, n0, ncols);
             const int co = m0 + r;
-            const bool valid = co < p.Nz;
+            bool valid = co < p.Nz;
             float* row = p.dw + (static_cast<long long>(tap) * p.Nz + co) * p.ldk + p.koff + n0;
+            if (p.stacked) {
+                // row r = (tap within the group, source channel); column = dz channel
+                const int g = r / p.Csrc, c = r - g * p.Csrc;
+                const int tp = tap * p.G + g;
+                valid = tp < p.ksize * p.ksize;
+                row = p.dw + (static_cast<long long>(tp) * p.Nz + n0) * p.ldk + p.koff + c;
+            }
             mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 800 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
@@ -223,7 +256,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                 uint32_t v[16];
                 tmem_ld16(t_row + c16 * 16, v);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid && p.stacked) {
+                    // transposed store: consecutive lanes hold consecutive source channels
+                    float* o = row + static_cast<long long>(c16) * 16 * p.ldk;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (p.splits > 1)
+                            red_add_f32(o + j * p.ldk, __uint_as_float(v[j]));
+                        else
+                            o[j * p.ldk] = __uint_as_float(v[j]);
+                    }
+                } else if (valid) {
                     float* o = row + c16 * 16;
                     if (p.splits > 1) {
 #pragma unroll
@@ -290,9 +333,7 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     WgradParams p = {};
     p.T = T; p.B = B; p.H = H; p.W = W;
     p.Nz = Nz; p.Csrc = Csrc; p.ksize = ksize; p.pad = ksize / 2;
-    p.cwA = chunk_width(Nz);
-    p.cwB = chunk_width(Csrc);
-    if (p.cwA == 0 || p.cwB == 0) {
+    if (chunk_width(Nz) == 0 || chunk_width(Csrc) == 0) {
         set_last_error("wgrad_tc: channels Nz=%d Csrc=%d not multiples of 16", Nz, Csrc);
         return B200_ERR_SHAPE;
     }
@@ -308,14 +349,31 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     p.Wt = mt.Wt; p.Ht = mt.Ht; p.Bt = mt.Bt;
     p.tiles_w = mt.tiles_w; p.tiles_h = mt.tiles_h; p.tiles_b = mt.tiles_b;
     p.num_rblocks = T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
-    const int block_n = Csrc > 128 ? 256 : (Csrc > 64 ? 128 : 64);
-    p.num_m_tiles = (Nz + WG_BLOCK_M - 1) / WG_BLOCK_M;
-    p.num_n_tiles = (Csrc + block_n - 1) / block_n;
-    p.out_tiles = ksize * ksize * p.num_m_tiles * p.num_n_tiles;
-    // reduction split: aim for >= 2 waves of work units, at least 8 reduction blocks per unit
-    int want = (2 * num_sms() + p.out_tiles - 1) / p.out_tiles;
+    const int taps = ksize * ksize;
+    // few source channels: stack G taps of the source along M, dz becomes the N operand
+    p.stacked = (Csrc == 16 || Csrc == 32 || Csrc == 64) && taps > 1 ? 1 : 0;
+    int block_n;
+    if (p.stacked) {
+        p.G = WG_BLOCK_M / Csrc;
+        p.cwA = Csrc;
+        p.cwB = chunk_width(Nz);
+        block_n = Nz > 128 ? 256 : (Nz > 64 ? 128 : 64);
+        p.num_m_tiles = 1;
+        p.num_n_tiles = (Nz + block_n - 1) / block_n;
+        p.out_tiles = ((taps + p.G - 1) / p.G) * p.num_n_tiles;
+    } else {
+        p.G = 1;
+        p.cwA = chunk_width(Nz);
+        p.cwB = chunk_width(Csrc);
+        block_n = Csrc > 128 ? 256 : (Csrc > 64 ? 128 : 64);
+        p.num_m_tiles = (Nz + WG_BLOCK_M - 1) / WG_BLOCK_M;
+        p.num_n_tiles = (Csrc + block_n - 1) / block_n;
+        p.out_tiles = taps * p.num_m_tiles * p.num_n_tiles;
+    }
+    // reduction split: fill two waves of CTAs without spilling into a third (floor, not ceil), and
+    // keep at least 8 reduction blocks per unit
+    int splits = (2 * num_sms()) / p.out_tiles;
     int max_splits = (p.num_rblocks + 7) / 8;
-    int splits = want < 1 ? 1 : want;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.rb_per_split = (p.num_rblocks + splits - 1) / splits;
@@ -324,9 +382,9 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     p.err_flag = device_error_flag();
 
     CUtensorMap tz, ts;
-    int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.cwA, mt.Wt, mt.Ht, mt.Bt);
+    int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.stacked ? p.cwB : p.cwA, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
-    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.cwB, mt.Wt, mt.Ht, mt.Bt);
+    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.stacked ? p.cwA : p.cwB, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
     switch (block_n) {
         case 256: return launch_wgrad_impl<256>(tz, ts, p, stream);

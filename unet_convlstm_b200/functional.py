@@ -104,8 +104,9 @@ class ConvBnRelu(torch.autograd.Function):
         C0 = x0.shape[-1]
         C1 = 0 if x1 is None else x1.shape[-1]
         K, ks = weight.shape[1], weight.shape[2]
-        dz, dgamma, dbeta = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training)
-        dbias = ops.colsum(T * B * H * W, dz, N) if ctx.has_bias else None
+        # the conv-bias gradient comes out of the BatchNorm sums in closed form (zero in training mode)
+        dz, dgamma, dbeta, dbias = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
+                                                   ctx.has_bias)
         # weight gradient, batched over all T*B images
         dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
         ops.conv_wgrad(dz, x0, ks, dwp, 0)

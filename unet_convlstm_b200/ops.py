@@ -255,8 +255,8 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
     return y, (mean, rstd, scale, shift, tstride)
 
 
-def bn_relu_bwd(z, dy, stats, training):
-    """Returns (dz, dgamma, dbeta)."""
+def bn_relu_bwd(z, dy, stats, training, want_dbias=False):
+    """Returns (dz, dgamma, dbeta, dconv_bias)."""
     _chk(z, "z"), _chk(dy, "dy")
     mean, rstd, scale, shift, tstride = stats
     T, B, H, W, C = z.shape
@@ -268,12 +268,13 @@ def bn_relu_bwd(z, dy, stats, training):
     coef = torch.empty((2, T, C), device=dev, dtype=torch.float32)
     dgamma = torch.empty(C, device=dev, dtype=torch.float32)
     dbeta = torch.empty(C, device=dev, dtype=torch.float32)
-    _lib.call("b200_bn_bwd_finalize", _p(ws[0]), _p(ws[1]), T, P, C, int(training), _p(coef[0]), _p(coef[1]),
-              _p(dgamma), _p(dbeta), 0, _st())
+    dcb = torch.empty(C, device=dev, dtype=torch.float32) if want_dbias else None
+    _lib.call("b200_bn_bwd_finalize", _p(ws[0]), _p(ws[1]), T, P, C, int(training), _p(scale), _p(coef[0]),
+              _p(coef[1]), _p(dgamma), _p(dbeta), _p(dcb), 0, _st())
     dz = torch.empty_like(z)
     _lib.call("b200_bn_relu_bwd_apply", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), _p(coef[0]),
               _p(coef[1]), _p(dz), T, P, C, tstride, _f32(z), _st())
-    return dz, dgamma, dbeta
+    return dz, dgamma, dbeta, dcb
 
 
 # ------------------------------------------------------------------------------------------------
