@@ -256,6 +256,35 @@ def run_b200_arm(args):
     for _ in range(args.warmup):
         step(x_dev, y_dev)
 
+    if args.breakdown:
+        # one instrumented step: CUDA events around every C-ABI call (adds event overhead; the per-kernel
+        # numbers it prints are for orientation, the judged ones come from the plain timed region + ncu)
+        _lib.TIMER = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(x_dev, y_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ev, _lib.TIMER = _lib.TIMER, None
+        agg = {}
+        for label, a, b, work in ev:
+            d = agg.setdefault(label, [0, 0.0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+            if work is not None:
+                d[2] += work[0] or 0.0
+                d[3] += work[1] or 0.0
+        tot = sum(d[1] for d in agg.values())
+        print(f"# breakdown of one step: {e0.elapsed_time(e1):.1f} ms wall, {tot:.1f} ms inside {len(ev)} C-ABI calls",
+              file=sys.stderr)
+        for label, d in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            rate = ""
+            if d[2]:
+                rate = f"{d[2] / d[1] / 1e9:8.1f} TFLOP/s"
+            elif d[3]:
+                rate = f"{d[3] / d[1] / 1e6:8.1f} GB/s"
+            print(f"# {d[1]:9.3f} ms {100 * d[1] / tot:5.1f}% x{d[0]:<4d} {rate:>18s}  {label}", file=sys.stderr)
+
     clk_path = os.path.join(ROOT, "gpurun_out", f"bench_clocks_r{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
     proc, f = clocks_sampler_start(local, clk_path) if rank == 0 else (None, None)
@@ -346,6 +375,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=2, help="sequences in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
     ap.add_argument("--profile-steps", type=int, default=0, help="run 1 warm-up + N untimed steps and exit (for ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -85,9 +85,23 @@ def last_error() -> str:
     return lib().b200_last_error().decode()
 
 
-def call(name: str, *args):
+# When set to a list (bench.py --breakdown), every call is bracketed by CUDA events on the current
+# stream: entries are (label, start_event, end_event, work) with work = (flops, bytes) or None.
+TIMER = None
+
+
+def call(name: str, *args, tag: str = "", work=None):
     """Calls an int-returning entry point and raises on a non-zero status."""
+    timer = TIMER
+    if timer is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib(), name)(*args)
+    if timer is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        timer.append((name + (" " + tag if tag else ""), e0, e1, work))
     CALLS[name] = CALLS.get(name, 0) + 1
     if rc != 0:
         raise RuntimeError(f"{name} failed: rc={rc}: {last_error()}")

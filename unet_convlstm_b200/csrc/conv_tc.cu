@@ -126,31 +126,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
+        // One thread issues every copy, so the loop body is kept to a handful of instructions: the
+        // (tap, channel-chunk) index is carried by nested counters, never derived by division
+        // (with N = 64 tiles a K block is only 128 tensor-pipe cycles and a heavier producer loop
+        // becomes the bottleneck: profiles/r01_ncu_wgrad_stacked_issue_bound.txt).
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t a_dst = smem_base;
+            const uint32_t tx_bytes = a_bytes + b_bytes;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(p, tile, BLOCK_N);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / chunks;
-                    const int rem = kb - tap * chunks;
-                    const int ky = tap / p.ksize;
-                    const int kx = tap - ky * p.ksize;
-                    mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
-                    mbar_arrive_expect_tx(full_bar(stage), a_bytes + b_bytes);
-                    const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-                    if (rem < chunks0) {
-                        tma_load_5d(a_dst, &tm_a0, full_bar(stage), rem * p.kc, tc.w0 + kx - p.pad,
-                                    tc.h0 + ky - p.pad, tc.b0, tc.t);
-                    } else {
-                        tma_load_5d(a_dst, &tm_a1, full_bar(stage), (rem - chunks0) * p.kc,
-                                    tc.w0 + kx - p.pad, tc.h0 + ky - p.pad, tc.b0, tc.t);
+                int ky = 0, kx = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int cw = tc.w0 + kx - p.pad, chh = tc.h0 + ky - p.pad;
+                    int kofs = 0;
+                    for (int c = 0; c < chunks; ++c, kofs += p.kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
+                        const uint32_t fb = full_bar(stage);
+                        mbar_arrive_expect_tx(fb, tx_bytes);
+                        if (c < chunks0)
+                            tma_load_5d(a_dst, &tm_a0, fb, kofs, cw, chh, tc.b0, tc.t);
+                        else
+                            tma_load_5d(a_dst, &tm_a1, fb, kofs - p.C0, cw, chh, tc.b0, tc.t);
+                        tma_load_3d(a_dst + Cfg::A_BYTES, &tm_b, fb, kofs, tc.n0, tap);
+                        a_dst += Cfg::STAGE_BYTES;
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                            a_dst = smem_base;
+                        }
                     }
-                    tma_load_3d(b_dst, &tm_b, full_bar(stage), rem * p.kc, tc.n0, tap);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
+                    if (++kx == p.ksize) {
+                        kx = 0;
+                        ++ky;
                     }
                 }
             }
@@ -164,31 +173,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             const uint32_t layout_type = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
             const uint32_t sbo = 8u * row_bytes;
             const int mma_per_kb = p.kc / 16;
+            // descriptor = constant high part | (smem address >> 4); only the address changes per stage
+            const uint64_t desc_hi = make_smem_desc(0, 16, sbo, layout_type);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            uint32_t a_lo = (smem_base & 0x3FFFFu) >> 4;
+            const uint32_t a_lo0 = a_lo;
+            constexpr uint32_t STAGE_LO = Cfg::STAGE_BYTES >> 4, B_LO = Cfg::A_BYTES >> 4;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                uint32_t accum = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-                    const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, layout_type);
-                    const uint64_t bdesc = make_smem_desc(b_addr, 16, sbo, layout_type);
-#pragma unroll 4
-                    for (int k = 0; k < mma_per_kb; ++k) {
+                    const uint64_t adesc = desc_hi | a_lo;
+                    const uint64_t bdesc = desc_hi | (a_lo + B_LO);
+                    if (mma_per_kb == 4) {
                         // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in >>4 units
-                        umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                        umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                        umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                        umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                    } else {
+                        for (int k = 0; k < mma_per_kb; ++k)
+                            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                                      k == 0 ? accum : 1u);
                     }
+                    accum = 1u;
                     umma_commit(empty_bar(stage));  // frees the smem slot when the MMAs retire
+                    a_lo += STAGE_LO;
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
+                        a_lo = a_lo0;
                     }
                 }
                 umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue

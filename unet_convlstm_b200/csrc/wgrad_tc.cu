@@ -1,28 +1,33 @@
 // Weight-gradient GEMM on the sm_100a tensor cores (conv backward-weight, batched over the
 // whole sequence / frame batch):
 //
-//   dW[tap][n][koff + k] (+)= sum_{t, pixel p} dz[t, p, n] * src[t, p + tap, k]
+//   dW[tap][n][koff + c] (+)= sum_{t, pixel p} dz[t, p, n] * src[t, p + tap, c]
 //
 // i.e. the autograd weight gradient of nn.Conv2d (reference train/unet.py:19 for the ConvLSTM
 // gate conv -- summed over all T timesteps of BPTT --, :70-71 for the UNet blocks).
 //
-// GEMM view: M = 128 rows of dz channels, N = up to 256 source channels, reduction over pixels.
-// Both operands are read straight from their NHWC tensors, where the *channel* (M resp. N)
-// index is contiguous and the pixel (reduction) index is strided: both UMMA operands are
-// therefore "MN-major".  A TMA box {cw channels, Wt, Ht, Bt} lands in smem as [pixel][cw] rows
+// Both operands are read straight from their NHWC tensors, where the *channel* index is
+// contiguous and the pixel (reduction) index is strided: both UMMA operands are therefore
+// "MN-major".  A TMA box {cw channels, Wt, Ht, Bt} (64 pixels) lands in smem as [pixel][cw] rows
 // with the 128/64/32-byte swizzle, which is exactly the canonical MN-major layout
 //     ((8 elem, cw/8, m), (8 pixels, k)) : ((1, 8, LBO), (cw, SBO))
 // with SBO = 8 pixel rows and LBO = one whole box (next channel chunk).  The tap shift and the
 // zero padding are the TMA coordinates / out-of-bounds fill of the source box, as in conv_tc.cu.
 //
-// Stacked mode (source with 16/32/64 channels, the full-resolution UNet layers): an M tile of
-// 128 dz channels would be half empty and every tap would re-read dz, so the roles are swapped:
-// A = G = 128/Csrc tap-shifted source boxes stacked along M (rows = (tap, source channel)),
-// B = dz channels (N).  One unit then covers G taps with one dz load per K block.
+// The kernel is bound by the L2 -> shared-memory fill rate, not by the tensor pipe, so it is
+// organised to load as few bytes per MMA as possible:
+//   * dz does not depend on the tap.  One dz box (the "shared" operand S) is loaded per 64-pixel
+//     block and re-used by up to GU taps / tap groups, each with its own TMEM accumulator
+//     (GU * BLOCK_N <= 512 columns); only the tap-shifted source boxes (the "varying" operand V)
+//     are loaded per tap.  S and V live in two independent smem rings.
+//   * Normal mode: A = dz (M = 128 dz channels), B = source channels (N <= 256).
+//   * Stacked mode (source with 16/32/64 channels, the full-resolution UNet layers): an M tile of
+//     128 dz channels would be half empty, so the roles are swapped: A = G = 128/Csrc tap-shifted
+//     source boxes stacked along M (rows = (tap, source channel)), B = dz channels (N).
 //
-// Work units = (reduction split s) x (tap, M tile, N tile); partial sums of different splits
-// are combined with vectorised fp32 reductions (red.global.add.v4.f32) into the caller's
-// zero-initialised buffer.  Warp roles are those of conv_tc.cu.
+// Work units = (reduction split) x (tap-group set, S tile, V tile); partial sums of different splits
+// are combined with fp32 reductions (red.global.add) into the caller's zero-initialised buffer.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -36,28 +41,32 @@ struct WgradParams {
     int T, B, H, W;
     int Nz;          // channels of dz (rows of dW)
     int Csrc;        // channels of the source (columns written)
-    int ksize, pad;
-    int cwA, cwB;    // channel chunk widths (64/32/16)
+    int ksize, pad, taps;
+    int cwS, cwV;    // channel chunk widths (64/32/16) of dz / source boxes
     int Wt, Ht, Bt, tiles_w, tiles_h, tiles_b;  // 64-pixel box geometry
     int num_rblocks; // T * tiles_w * tiles_h * tiles_b
     int rb_per_split, splits;
-    int num_m_tiles, num_n_tiles, out_tiles;
-    int stacked;     // 1: A = tap-stacked source boxes (G taps x Csrc = 128 rows), B = dz; see below
-    int G;           // taps per unit in stacked mode
+    int G;           // taps per group (stacked mode: 128 / Csrc; normal mode: 1)
+    int ngroups;     // ceil(taps / G)
+    int GU;          // groups (accumulators) per unit
+    int ngsets;      // ceil(ngroups / GU)
+    int s_tiles, v_tiles, out_tiles;
     float* dw;       // [taps][Nz][ldk]
     long long ldk;
     int koff;
     int* err_flag;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STACKED>
 struct WgCfg {
-    static constexpr int A_BYTES = WG_BLOCK_M * WG_RB * 2;  // 16 KB
+    static constexpr int A_BYTES = WG_BLOCK_M * WG_RB * 2;  // 16 KB: the M = 128 operand
     static constexpr int B_BYTES = BLOCK_N * WG_RB * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = 2 * BLOCK_N;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int V_BYTES = STACKED ? A_BYTES : B_BYTES;  // varying (source) operand
+    static constexpr int S_BYTES = STACKED ? B_BYTES : A_BYTES;  // shared (dz) operand
+    static constexpr int SV = STACKED ? (BLOCK_N == 256 ? 6 : 8) : (BLOCK_N == 256 ? 5 : (BLOCK_N == 128 ? 6 : 8));
+    static constexpr int SS = STACKED ? (BLOCK_N == 64 ? 4 : 3) : (BLOCK_N == 256 ? 3 : 4);
+    static constexpr int MAX_GU = 512 / BLOCK_N;
+    static constexpr int SMEM_BYTES = SV * V_BYTES + SS * S_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -65,53 +74,93 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  "f"(d)
                  : "memory");
 }
-
 __device__ __forceinline__ void red_add_f32(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
-template <int BLOCK_N>
+struct WgUnit {
+    int split, gset, s0, v0, scols, vcols, ngr;
+};
+
+template <int BLOCK_N, bool STACKED>
+__device__ __forceinline__ WgUnit wg_decode(const WgradParams& p, int unit) {
+    WgUnit u;
+    u.split = unit / p.out_tiles;
+    int ot = unit - u.split * p.out_tiles;
+    const int vt = ot % p.v_tiles;
+    ot /= p.v_tiles;
+    const int st = ot % p.s_tiles;
+    u.gset = ot / p.s_tiles;
+    if (STACKED) {
+        u.s0 = st * BLOCK_N;  // dz channels are the N operand
+        u.scols = min(BLOCK_N, p.Nz - u.s0);
+        u.v0 = 0;
+        u.vcols = WG_BLOCK_M;
+    } else {
+        u.s0 = st * WG_BLOCK_M;  // dz channels are the M operand
+        u.scols = min(WG_BLOCK_M, p.Nz - u.s0);
+        u.v0 = vt * BLOCK_N;
+        u.vcols = min(BLOCK_N, p.Csrc - u.v0);
+    }
+    u.ngr = min(p.GU, p.ngroups - u.gset * p.GU);
+    return u;
+}
+
+template <int BLOCK_N, bool STACKED>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_src,
                 const WgradParams p) {
-    using Cfg = WgCfg<BLOCK_N>;
-    constexpr int STAGES = Cfg::STAGES;
+    using Cfg = WgCfg<BLOCK_N, STACKED>;
+    constexpr int SV = Cfg::SV, SS = Cfg::SS;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t v_base = smem_base;
+    const uint32_t s_base = smem_base + SV * Cfg::V_BYTES;
+    const uint32_t bar_base = s_base + SS * Cfg::S_BYTES;
+    auto vfull = [&](int s) { return bar_base + 8u * s; };
+    auto vempty = [&](int s) { return bar_base + 8u * (SV + s); };
+    auto sfull = [&](int s) { return bar_base + 8u * (2 * SV + s); };
+    auto sempty = [&](int s) { return bar_base + 8u * (2 * SV + SS + s); };
+    const uint32_t tfull = bar_base + 8u * (2 * SV + 2 * SS);
+    const uint32_t tempty = tfull + 8u;
+    const uint32_t tmem_ptr_addr = tfull + 16u;
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_units = p.out_tiles * p.splits;
-    const int boxesA = WG_BLOCK_M / p.cwA;
-    const uint32_t boxA_bytes = WG_RB * p.cwA * 2;
-    const uint32_t boxB_bytes = WG_RB * p.cwB * 2;
+    // A operand (M = 128): stacked -> source boxes, normal -> dz boxes
+    const int cwA = STACKED ? p.cwV : p.cwS;
+    const int cwB = STACKED ? p.cwS : p.cwV;
+    const uint32_t boxA_bytes = WG_RB * cwA * 2;
+    const uint32_t boxB_bytes = WG_RB * cwB * 2;
+    const uint32_t boxS_bytes = STACKED ? boxB_bytes : boxA_bytes;
+    const uint32_t boxV_bytes = STACKED ? boxA_bytes : boxB_bytes;
+    const int cwS = p.cwS, cwV = p.cwV;
+    int tmem_cols = 32;
+    while (tmem_cols < p.GU * BLOCK_N) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_dz);
         prefetch_tmap(&tm_src);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+        for (int s = 0; s < SV; ++s) {
+            mbar_init(vfull(s), 1);
+            mbar_init(vempty(s), 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);
+        for (int s = 0; s < SS; ++s) {
+            mbar_init(sfull(s), 1);
+            mbar_init(sempty(s), 1);
         }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+        tmem_alloc(tmem_ptr_addr, tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -119,176 +168,203 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
-    // unit -> (split, tap, m tile, n tile); n columns actually present in this N tile
-    auto decode = [&](int unit, int& split, int& tap, int& m0, int& n0, int& ncols) {
-        split = unit / p.out_tiles;
-        int ot = unit - split * p.out_tiles;
-        int nt = ot % p.num_n_tiles;
-        ot /= p.num_n_tiles;
-        int mt = ot % p.num_m_tiles;
-        tap = ot / p.num_m_tiles;
-        m0 = mt * WG_BLOCK_M;
-        n0 = nt * BLOCK_N;
-        // stacked mode: "tap" is the tap group, N runs over dz channels
-        ncols = min(BLOCK_N, (p.stacked ? p.Nz : p.Csrc) - n0);
-    };
-
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-                int split, tap, m0, n0, ncols;
-                decode(unit, split, tap, m0, n0, ncols);
-                const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-                const int boxesB = (ncols + p.cwB - 1) / p.cwB;
-                const int rb_begin = split * p.rb_per_split;
-                const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-                for (int rb = rb_begin; rb < rb_end; ++rb) {
-                    int m = rb;
-                    const int wt = m % p.tiles_w;
-                    m /= p.tiles_w;
-                    const int ht = m % p.tiles_h;
-                    m /= p.tiles_h;
-                    const int bt = m % p.tiles_b;
-                    const int t = m / p.tiles_b;
-                    const int w0 = wt * p.Wt, h0 = ht * p.Ht, b0 = bt * p.Bt;
-                    mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 500 + stage);
-                    mbar_arrive_expect_tx(full_bar(stage), boxesA * boxA_bytes + boxesB * boxB_bytes);
-                    const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-                    if (p.stacked) {
-                        const int taps = p.ksize * p.ksize;
-                        for (int i = 0; i < boxesA; ++i) {
-                            // taps beyond the filter repeat the last one; their rows are never stored
-                            const int tp = min(tap * p.G + i, taps - 1);
-                            const int sy = tp / p.ksize, sx = tp - sy * p.ksize;
-                            tma_load_5d(a_dst + i * boxA_bytes, &tm_src, full_bar(stage), 0, w0 + sx - p.pad,
-                                        h0 + sy - p.pad, b0, t);
-                        }
-                        for (int i = 0; i < boxesB; ++i)
-                            tma_load_5d(b_dst + i * boxB_bytes, &tm_dz, full_bar(stage), n0 + i * p.cwB, w0, h0,
-                                        b0, t);
-                    } else {
-                        for (int i = 0; i < boxesA; ++i)
-                            tma_load_5d(a_dst + i * boxA_bytes, &tm_dz, full_bar(stage), m0 + i * p.cwA, w0,
-                                        h0, b0, t);
-                        for (int i = 0; i < boxesB; ++i)
-                            tma_load_5d(b_dst + i * boxB_bytes, &tm_src, full_bar(stage), n0 + i * p.cwB,
-                                        w0 + kx - p.pad, h0 + ky - p.pad, b0, t);
+        // =================================== TMA producer ===================================
+        // The whole warp takes part: lane l owns one (tap group, box) pair of the varying operand --
+        // its tap shift is fixed for the unit -- and lanes 0..boxesS-1 the dz boxes, so the per-block
+        // work of each lane is a few adds and one copy; the pixel-block coordinates are carried by
+        // nested counters (no divisions in the loop).
+        int sv = 0, ss = 0;
+        uint32_t pv = 0, ps = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const WgUnit u = wg_decode<BLOCK_N, STACKED>(p, unit);
+            const int boxesS = (u.scols + cwS - 1) / cwS;
+            const int boxesV = STACKED ? p.G : (u.vcols + cwV - 1) / cwV;
+            const int rb_begin = u.split * p.rb_per_split;
+            const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
+            // this lane's varying box: group my_g, box my_i
+            const int my_g = lane / boxesV, my_i = lane - my_g * boxesV;
+            const bool v_lane = my_g < u.ngr;
+            int my_dx = 0, my_dy = 0, my_c = 0;
+            if (v_lane) {
+                const int grp = u.gset * p.GU + my_g;
+                // stacked: taps beyond the filter repeat the last one; their rows are never stored
+                const int tp = STACKED ? min(grp * p.G + my_i, p.taps - 1) : grp;
+                const int sy = tp / p.ksize;
+                my_dy = sy - p.pad;
+                my_dx = tp - sy * p.ksize - p.pad;
+                my_c = STACKED ? 0 : u.v0 + my_i * cwV;
+            }
+            const uint32_t my_voff = my_i * boxV_bytes;
+            const bool s_lane = lane < boxesS;
+            const int my_sc = u.s0 + lane * cwS;
+            const uint32_t s_tx = boxesS * boxS_bytes, v_tx = boxesV * boxV_bytes;
+            // pixel-block counters
+            int m = rb_begin;
+            int wt = m % p.tiles_w;
+            m /= p.tiles_w;
+            int ht = m % p.tiles_h;
+            m /= p.tiles_h;
+            int bt = m % p.tiles_b;
+            int t = m / p.tiles_b;
+            for (int rb = rb_begin; rb < rb_end; ++rb) {
+                const int w0 = wt * p.Wt, h0 = ht * p.Ht, b0 = bt * p.Bt;
+                // shared operand: the dz box(es) of this pixel block
+                if (lane == 0) {
+                    mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 500 + ss);
+                    mbar_arrive_expect_tx(sfull(ss), s_tx);
+                }
+                __syncwarp();
+                if (s_lane)
+                    tma_load_5d(s_base + ss * Cfg::S_BYTES + lane * boxS_bytes, &tm_dz, sfull(ss), my_sc, w0, h0, b0, t);
+                if (++ss == SS) {
+                    ss = 0;
+                    ps ^= 1u;
+                }
+                // varying operand: one stage per tap group
+                for (int g = 0; g < u.ngr; ++g) {
+                    if (lane == 0) {
+                        mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
+                        mbar_arrive_expect_tx(vfull(sv), v_tx);
                     }
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
+                    __syncwarp();
+                    if (v_lane && my_g == g)
+                        tma_load_5d(v_base + sv * Cfg::V_BYTES + my_voff, &tm_src, vfull(sv), my_c, w0 + my_dx,
+                                    h0 + my_dy, b0, t);
+                    if (++sv == SV) {
+                        sv = 0;
+                        pv ^= 1u;
+                    }
+                }
+                if (++wt == p.tiles_w) {
+                    wt = 0;
+                    if (++ht == p.tiles_h) {
+                        ht = 0;
+                        if (++bt == p.tiles_b) {
+                            bt = 0;
+                            ++t;
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
+        // =================================== MMA issuer =====================================
         if (lane == 0) {
-            const uint32_t ltA = (p.cwA == 64) ? 2u : (p.cwA == 32 ? 4u : 6u);
-            const uint32_t ltB = (p.cwB == 64) ? 2u : (p.cwB == 32 ? 4u : 6u);
-            const uint32_t sboA = 8u * p.cwA * 2, sboB = 8u * p.cwB * 2;
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            const uint32_t ltA = (cwA == 64) ? 2u : (cwA == 32 ? 4u : 6u);
+            const uint32_t ltB = (cwB == 64) ? 2u : (cwB == 32 ? 4u : 6u);
+            // descriptor = constant high part | (smem address >> 4); 16 pixels (one MMA K step) further
+            // down the box = two 8-row atoms = 16 * cw * 2 bytes
+            const uint64_t hiA = make_smem_desc(0, boxA_bytes, 8u * cwA * 2, ltA);
+            const uint64_t hiB = make_smem_desc(0, boxB_bytes, 8u * cwB * 2, ltB);
+            const uint32_t stepA = (16u * cwA * 2) >> 4, stepB = (16u * cwB * 2) >> 4;
+            const uint32_t v_lo0 = (v_base & 0x3FFFFu) >> 4, s_lo0 = (s_base & 0x3FFFFu) >> 4;
+            int sv = 0, ss = 0;
+            uint32_t pv = 0, ps = 0, pt = 0;
             for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-                int split, tap, m0, n0, ncols;
-                decode(unit, split, tap, m0, n0, ncols);
-                const int nmma = ((ncols + p.cwB - 1) / p.cwB) * p.cwB;  // whole loaded boxes
+                const WgUnit u = wg_decode<BLOCK_N, STACKED>(p, unit);
+                const int ncols = STACKED ? u.scols : u.vcols;
+                const int nmma = ((ncols + cwB - 1) / cwB) * cwB;  // whole loaded boxes
                 const uint32_t idesc = make_idesc_bf16(WG_BLOCK_M, nmma, 1, 1);
-                const int rb_begin = split * p.rb_per_split;
+                const int rb_begin = u.split * p.rb_per_split;
                 const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 700 + acc);
+                mbar_wait(tempty, pt ^ 1u, p.err_flag, 700);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                uint32_t accum = 0;
                 for (int rb = rb_begin; rb < rb_end; ++rb) {
-                    mbar_wait(full_bar(stage), phase, p.err_flag, 600 + stage);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < WG_RB / 16; ++k) {
-                        // 16 pixels = two 8-row atoms further down the box
-                        const uint64_t adesc =
-                            make_smem_desc(a_addr + k * 16 * p.cwA * 2, boxA_bytes, sboA, ltA);
-                        const uint64_t bdesc =
-                            make_smem_desc(b_addr + k * 16 * p.cwB * 2, boxB_bytes, sboB, ltB);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, (rb > rb_begin || k > 0) ? 1u : 0u);
+                    mbar_wait(sfull(ss), ps, p.err_flag, 600 + ss);
+                    const uint32_t s_lo = s_lo0 + ss * (Cfg::S_BYTES >> 4);
+                    uint32_t d_tmem = tmem_base;
+                    for (int g = 0; g < u.ngr; ++g, d_tmem += BLOCK_N) {
+                        mbar_wait(vfull(sv), pv, p.err_flag, 620 + sv);
+                        tc_fence_after();
+                        const uint32_t v_lo = v_lo0 + sv * (Cfg::V_BYTES >> 4);
+                        const uint64_t adesc = hiA | (STACKED ? v_lo : s_lo);
+                        const uint64_t bdesc = hiB | (STACKED ? s_lo : v_lo);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                        umma_bf16(d_tmem, adesc + stepA, bdesc + stepB, idesc, 1u);
+                        umma_bf16(d_tmem, adesc + 2 * stepA, bdesc + 2 * stepB, idesc, 1u);
+                        umma_bf16(d_tmem, adesc + 3 * stepA, bdesc + 3 * stepB, idesc, 1u);
+                        umma_commit(vempty(sv));
+                        if (++sv == SV) {
+                            sv = 0;
+                            pv ^= 1u;
+                        }
                     }
-                    umma_commit(empty_bar(stage));
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
+                    accum = 1u;
+                    umma_commit(sempty(ss));  // after the MMAs of every group that read this dz box
+                    if (++ss == SS) {
+                        ss = 0;
+                        ps ^= 1u;
                     }
                 }
-                umma_commit(tfull_bar(acc));
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1u;
-                }
+                umma_commit(tfull);
+                pt ^= 1u;
             }
         }
     } else if (warp >= 4) {
+        // =================================== epilogue =======================================
         const int q = warp - 4;
         const int r = q * 32 + lane;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t pt = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            int split, tap, m0, n0, ncols;
-            decode(unit, split, tap, m0, n0, ncols);
-            const int co = m0 + r;
-            bool valid = co < p.Nz;
-            float* row = p.dw + (static_cast<long long>(tap) * p.Nz + co) * p.ldk + p.koff + n0;
-            if (p.stacked) {
-                // row r = (tap within the group, source channel); column = dz channel
-                const int g = r / p.Csrc, c = r - g * p.Csrc;
-                const int tp = tap * p.G + g;
-                valid = tp < p.ksize * p.ksize;
-                row = p.dw + (static_cast<long long>(tp) * p.Nz + n0) * p.ldk + p.koff + c;
-            }
-            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 800 + acc);
+            const WgUnit u = wg_decode<BLOCK_N, STACKED>(p, unit);
+            const int ncols = STACKED ? u.scols : u.vcols;
+            mbar_wait(tfull, pt, p.err_flag, 800);
+            pt ^= 1u;
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
+            for (int g = 0; g < u.ngr; ++g) {
+                const int grp = u.gset * p.GU + g;
+                bool valid;
+                float* row;
+                if (STACKED) {
+                    // row r = (tap within the group, source channel); column = dz channel
+                    const int gi = r / p.Csrc, c = r - gi * p.Csrc;
+                    const int tp = grp * p.G + gi;
+                    valid = tp < p.taps;
+                    row = p.dw + (static_cast<long long>(tp) * p.Nz + u.s0) * p.ldk + p.koff + c;
+                } else {
+                    const int n = u.s0 + r;
+                    valid = n < p.Nz;
+                    row = p.dw + (static_cast<long long>(grp) * p.Nz + n) * p.ldk + p.koff + u.v0;
+                }
+                const uint32_t t_row = tmem_base + g * BLOCK_N + (uint32_t(q * 32) << 16);
 #pragma unroll 1
-            for (int c16 = 0; c16 * 16 < ncols; ++c16) {
-                uint32_t v[16];
-                tmem_ld16(t_row + c16 * 16, v);
-                tmem_ld_wait();
-                if (valid && p.stacked) {
-                    // transposed store: consecutive lanes hold consecutive source channels
-                    float* o = row + static_cast<long long>(c16) * 16 * p.ldk;
+                for (int c16 = 0; c16 * 16 < ncols; ++c16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + c16 * 16, v);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    if (STACKED) {
+                        // transposed store: consecutive lanes hold consecutive source channels
+                        float* o = row + static_cast<long long>(c16) * 16 * p.ldk;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (p.splits > 1)
-                            red_add_f32(o + j * p.ldk, __uint_as_float(v[j]));
-                        else
-                            o[j * p.ldk] = __uint_as_float(v[j]);
-                    }
-                } else if (valid) {
-                    float* o = row + c16 * 16;
-                    if (p.splits > 1) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            red_add_v4(o + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        for (int j = 0; j < 16; ++j) {
+                            if (p.splits > 1)
+                                red_add_f32(o + j * p.ldk, __uint_as_float(v[j]));
+                            else
+                                o[j * p.ldk] = __uint_as_float(v[j]);
+                        }
                     } else {
+                        float* o = row + c16 * 16;
+                        if (p.splits > 1) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<float4*>(o)[j] =
-                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            for (int j = 0; j < 4; ++j)
+                                red_add_v4(o + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<float4*>(o)[j] =
+                                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1u;
-            }
+            if (lane == 0) mbar_arrive(tempty);
         }
     }
 
@@ -296,15 +372,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STACKED>
 static int launch_wgrad_impl(const CUtensorMap& tz, const CUtensorMap& ts, const WgradParams& p,
                              cudaStream_t stream) {
-    using Cfg = WgCfg<BLOCK_N>;
-    auto kern = wgrad_tc_kernel<BLOCK_N>;
+    using Cfg = WgCfg<BLOCK_N, STACKED>;
+    auto kern = wgrad_tc_kernel<BLOCK_N, STACKED>;
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -325,15 +401,15 @@ static int chunk_width(int C) {
     return 0;
 }
 
-// dw must be zero-initialised by the caller when more than one reduction split is used; the
-// function reports the split count through *splits_out so the caller can tell (it is >1 only
-// for layers with few output tiles).  To keep the contract simple the caller always zeroes.
+// dw must be zero-initialised by the caller (partial sums of the reduction splits are added to it).
 int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
                     int ksize, float* dw, long long ldk, int koff, cudaStream_t stream) {
     WgradParams p = {};
     p.T = T; p.B = B; p.H = H; p.W = W;
-    p.Nz = Nz; p.Csrc = Csrc; p.ksize = ksize; p.pad = ksize / 2;
-    if (chunk_width(Nz) == 0 || chunk_width(Csrc) == 0) {
+    p.Nz = Nz; p.Csrc = Csrc; p.ksize = ksize; p.pad = ksize / 2; p.taps = ksize * ksize;
+    p.cwS = chunk_width(Nz);
+    p.cwV = chunk_width(Csrc);
+    if (p.cwS == 0 || p.cwV == 0) {
         set_last_error("wgrad_tc: channels Nz=%d Csrc=%d not multiples of 16", Nz, Csrc);
         return B200_ERR_SHAPE;
     }
@@ -349,47 +425,68 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     p.Wt = mt.Wt; p.Ht = mt.Ht; p.Bt = mt.Bt;
     p.tiles_w = mt.tiles_w; p.tiles_h = mt.tiles_h; p.tiles_b = mt.tiles_b;
     p.num_rblocks = T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
-    const int taps = ksize * ksize;
     // few source channels: stack G taps of the source along M, dz becomes the N operand
-    p.stacked = (Csrc == 16 || Csrc == 32 || Csrc == 64) && taps > 1 ? 1 : 0;
+    const bool stacked = (Csrc == 16 || Csrc == 32 || Csrc == 64) && p.taps > 1;
     int block_n;
-    if (p.stacked) {
+    if (stacked) {
         p.G = WG_BLOCK_M / Csrc;
-        p.cwA = Csrc;
-        p.cwB = chunk_width(Nz);
+        p.cwV = Csrc;
         block_n = Nz > 128 ? 256 : (Nz > 64 ? 128 : 64);
-        p.num_m_tiles = 1;
-        p.num_n_tiles = (Nz + block_n - 1) / block_n;
-        p.out_tiles = ((taps + p.G - 1) / p.G) * p.num_n_tiles;
+        p.s_tiles = (Nz + block_n - 1) / block_n;
+        p.v_tiles = 1;
     } else {
         p.G = 1;
-        p.cwA = chunk_width(Nz);
-        p.cwB = chunk_width(Csrc);
         block_n = Csrc > 128 ? 256 : (Csrc > 64 ? 128 : 64);
-        p.num_m_tiles = (Nz + WG_BLOCK_M - 1) / WG_BLOCK_M;
-        p.num_n_tiles = (Csrc + block_n - 1) / block_n;
-        p.out_tiles = taps * p.num_m_tiles * p.num_n_tiles;
+        p.s_tiles = (Nz + WG_BLOCK_M - 1) / WG_BLOCK_M;
+        p.v_tiles = (Csrc + block_n - 1) / block_n;
     }
-    // reduction split: fill two waves of CTAs without spilling into a third (floor, not ceil), and
-    // keep at least 8 reduction blocks per unit
-    int splits = (2 * num_sms()) / p.out_tiles;
+    p.ngroups = (p.taps + p.G - 1) / p.G;
+    p.GU = 512 / block_n;
+    if (p.GU > p.ngroups) p.GU = p.ngroups;
+    // the producer warp gives every (group, box) pair of the varying operand its own lane
+    const int boxes_v = stacked ? p.G : ((Csrc < block_n ? Csrc : block_n) + p.cwV - 1) / p.cwV;
+    while (p.GU > 1 && p.GU * boxes_v > 32) --p.GU;
+    // balance the group sets (e.g. 9 taps, at most 4 accumulators -> 3+3+3 rather than 4+4+1)
+    p.ngsets = (p.ngroups + p.GU - 1) / p.GU;
+    p.GU = (p.ngroups + p.ngsets - 1) / p.ngsets;
+    p.out_tiles = p.ngsets * p.s_tiles * p.v_tiles;
+    // reduction split: the split count that minimises (waves of CTAs) / split, smallest such count;
+    // at least 8 reduction blocks per unit
+    const int nsm = num_sms();
     int max_splits = (p.num_rblocks + 7) / 8;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    p.rb_per_split = (p.num_rblocks + splits - 1) / splits;
+    if (max_splits > 4 * nsm) max_splits = 4 * nsm;
+    if (max_splits < 1) max_splits = 1;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= max_splits; ++s) {
+        const long long units = static_cast<long long>(p.out_tiles) * s;
+        const double cost = static_cast<double>((units + nsm - 1) / nsm) / s;
+        if (cost < best_cost * 0.97) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    p.rb_per_split = (p.num_rblocks + best - 1) / best;
     p.splits = (p.num_rblocks + p.rb_per_split - 1) / p.rb_per_split;
     p.dw = dw; p.ldk = ldk; p.koff = koff;
     p.err_flag = device_error_flag();
 
     CUtensorMap tz, ts;
-    int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.stacked ? p.cwB : p.cwA, mt.Wt, mt.Ht, mt.Bt);
+    int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.cwS, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
-    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.stacked ? p.cwA : p.cwB, mt.Wt, mt.Ht, mt.Bt);
+    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.cwV, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
+    if (stacked) {
+        switch (block_n) {
+            case 256: return launch_wgrad_impl<256, true>(tz, ts, p, stream);
+            case 128: return launch_wgrad_impl<128, true>(tz, ts, p, stream);
+            default: return launch_wgrad_impl<64, true>(tz, ts, p, stream);
+        }
+    }
     switch (block_n) {
-        case 256: return launch_wgrad_impl<256>(tz, ts, p, stream);
-        case 128: return launch_wgrad_impl<128>(tz, ts, p, stream);
-        default: return launch_wgrad_impl<64>(tz, ts, p, stream);
+        case 256: return launch_wgrad_impl<256, false>(tz, ts, p, stream);
+        case 128: return launch_wgrad_impl<128, false>(tz, ts, p, stream);
+        default: return launch_wgrad_impl<64, false>(tz, ts, p, stream);
     }
 }
 

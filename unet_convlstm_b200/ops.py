@@ -195,12 +195,15 @@ def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False):
     if out1 is not None and out1.dtype != out0.dtype:
         raise ValueError("conv_fwd: out0/out1 dtypes differ")
     ld1 = 0 if out1 is None else out1.shape[-1]
+    tag = f"K{C0 + C1} N{N} {H}x{W} k{ksize}"
+    work = (2.0 * T * B * H * W * ksize * ksize * (C0 + C1) * N, None)
     if tc_conv_ok(x0, x1, N) and split % 16 == 0 and out0.shape[-1] % 8 == 0 and ld1 % 8 == 0:
         _lib.call("b200_conv_tc_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(bias), N, ksize, _p(out0),
-                  out0.shape[-1], split, _p(out1), ld1, _f32(out0), int(relu), 0, _st())
+                  out0.shape[-1], split, _p(out1), ld1, _f32(out0), int(relu), 0, _st(), tag=tag, work=work)
     else:
         _lib.call("b200_conv_simt_fwd", _p(x0), C0, _p(x1), C1, T * B, H, W, _p(wp), _p(bias), N, ksize,
-                  _p(out0), out0.shape[-1], split, _p(out1), ld1, _f32(x0), _f32(out0), int(relu), _st())
+                  _p(out0), out0.shape[-1], split, _p(out1), ld1, _f32(x0), _f32(out0), int(relu), _st(),
+                  tag=tag, work=work)
     return out0
 
 
@@ -210,11 +213,15 @@ def conv_wgrad(dz, src, ksize, dw, koff):
     T, B, H, W, Nz = dz.shape
     Cs = src.shape[-1]
     ldk = dw.shape[2]
+    tag = f"Nz{Nz} C{Cs} {H}x{W} k{ksize} T{T}"
+    work = (2.0 * T * B * H * W * ksize * ksize * Cs * Nz, None)
     if dz.dtype == torch.bfloat16 and ldk % 4 == 0 and koff % 4 == 0 and \
             _lib.supported("b200_wgrad_tc_supported", B, H, W, Nz, Cs):
-        _lib.call("b200_wgrad_tc", _p(dz), Nz, _p(src), Cs, T, B, H, W, ksize, _p(dw), ldk, koff, _st())
+        _lib.call("b200_wgrad_tc", _p(dz), Nz, _p(src), Cs, T, B, H, W, ksize, _p(dw), ldk, koff, _st(),
+                  tag=tag, work=work)
     else:
-        _lib.call("b200_wgrad_simt", _p(dz), Nz, _p(src), Cs, T * B, H, W, ksize, _p(dw), ldk, koff, _f32(dz), _st())
+        _lib.call("b200_wgrad_simt", _p(dz), Nz, _p(src), Cs, T * B, H, W, ksize, _p(dw), ldk, koff, _f32(dz), _st(),
+                  tag=tag, work=work)
     return dw
 
 
@@ -243,7 +250,8 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
     shift = torch.empty_like(mean)
     if training:
         ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
-        _lib.call("b200_bn_stats", _p(z), T, P, C, _f32(z), _p(ws[0]), _p(ws[1]), _st())
+        _lib.call("b200_bn_stats", _p(z), T, P, C, _f32(z), _p(ws[0]), _p(ws[1]), _st(),
+                  tag=f"C{C} {H}x{W}", work=(None, z.numel() * z.element_size()))
         _lib.call("b200_bn_finalize", _p(ws[0]), _p(ws[1]), T, P, C, _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), eps, momentum, 1, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     else:
@@ -251,7 +259,8 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
                   _p(running_var), eps, momentum, 0, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     tstride = C if training else 0
     y = torch.empty_like(z)
-    _lib.call("b200_bn_relu_apply", _p(z), _p(scale), _p(shift), _p(y), T, P, C, tstride, 1, _f32(z), _st())
+    _lib.call("b200_bn_relu_apply", _p(z), _p(scale), _p(shift), _p(y), T, P, C, tstride, 1, _f32(z), _st(),
+              tag=f"C{C} {H}x{W}", work=(None, 2 * z.numel() * z.element_size()))
     return y, (mean, rstd, scale, shift, tstride)
 
 
@@ -264,7 +273,7 @@ def bn_relu_bwd(z, dy, stats, training, want_dbias=False):
     dev = z.device
     ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
     _lib.call("b200_bn_relu_bwd_reduce", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), T, P, C, tstride,
-              _f32(z), _p(ws[0]), _p(ws[1]), _st())
+              _f32(z), _p(ws[0]), _p(ws[1]), _st(), tag=f"C{C} {H}x{W}", work=(None, 2 * z.numel() * z.element_size()))
     coef = torch.empty((2, T, C), device=dev, dtype=torch.float32)
     dgamma = torch.empty(C, device=dev, dtype=torch.float32)
     dbeta = torch.empty(C, device=dev, dtype=torch.float32)
@@ -273,7 +282,8 @@ def bn_relu_bwd(z, dy, stats, training, want_dbias=False):
               _p(coef[1]), _p(dgamma), _p(dbeta), _p(dcb), 0, _st())
     dz = torch.empty_like(z)
     _lib.call("b200_bn_relu_bwd_apply", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), _p(coef[0]),
-              _p(coef[1]), _p(dz), T, P, C, tstride, _f32(z), _st())
+              _p(coef[1]), _p(dz), T, P, C, tstride, _f32(z), _st(), tag=f"C{C} {H}x{W}",
+              work=(None, 3 * z.numel() * z.element_size()))
     return dz, dgamma, dbeta, dcb
 
 
@@ -363,8 +373,10 @@ def lstm_cell_fwd_fused(x_t, h_prev, c_prev, wp_il, bias_il, c_next, h_next, gat
     if timer is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
+    kin_ = Cin + (Ch if h_prev is not None else 0)
     _lib.call("b200_convlstm_cell_fwd_tc", _p(x_t), Cin, _p(h_prev), Ch, B, H, W, _p(wp_il), _p(bias_il),
-              _p(c_prev), _p(c_next), _p(h_next), _p(gates), ksize, _st())
+              _p(c_prev), _p(c_next), _p(h_next), _p(gates), ksize, _st(), tag=f"Ch{Ch} {H}x{W}",
+              work=(2.0 * B * H * W * ksize * ksize * kin_ * 4 * Ch, None))
     if timer is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
@@ -387,5 +399,7 @@ def lstm_cell_fwd_unfused(x_t, h_prev, c_prev, wp, bias, c_next, h_next, gates, 
 
 def lstm_gates_bwd(gates, c_prev, c_next, dh_a, dh_b, dc_next, dz, dc_prev):
     B, H, W, Ch = c_next.shape
+    es = gates.element_size()
+    nb = B * H * W * Ch * (4 * es + 8 + es * (1 + (dh_b is not None)) + 4 * (dc_next is not None) + 4 * es + 4)
     _lib.call("b200_lstm_gates_bwd", _p(gates), _p(c_prev), _p(c_next), _p(dh_a), _p(dh_b), _p(dc_next), _p(dz),
-              _p(dc_prev), B * H * W, Ch, _f32(gates), _st())
+              _p(dc_prev), B * H * W, Ch, _f32(gates), _st(), tag=f"Ch{Ch} {H}x{W}", work=(None, nb))
