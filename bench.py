@@ -339,7 +339,8 @@ def run_b200_arm(args):
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4, "d2h_bytes_per_step": 4},
             "fwd_bwd_only": {"value": world * args.batch / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb},
             "gpu_launches": launches,
-            "roofline": {"kernel": "conv_tc_kernel<256, EPI_LSTM> (fused ConvLSTM gate conv + cell update, forward)",
+            "roofline": {"kernel": "conv_tc_kernel<256, EPI_LSTM>: fused ConvLSTM gate conv + gate math + c/h update, "
+                                   "forward, one timestep-persistent launch per layer (T steps)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach / peak_tf) if ach else None, "traffic": traffic, "peak_source": peak_src,
                          "launches_timed": len(full),

@@ -49,6 +49,17 @@ int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch
                               const void* wpacked, const float* bias_packed, const float* c_prev,
                               float* c_next, void* h_next, void* gates_out, int ksize, void* stream);
 
+/* Whole-sequence forward of one ConvLSTM layer, the t-loop of ConvLSTM.forward (unet.py:52-57), as ONE
+ * timestep-persistent cooperative kernel: the grid iterates over t = 0..T-1, h_t / c_t stay in the
+ * (L2-resident) state buffers, a grid-wide counter separates the steps, no host round trip per step.
+ * x_seq: bf16 [T][B][H][W][Cin]; h_all: bf16 [T+1][B][H][W][Ch], slot 0 = initial state (ignored when
+ * have_h0 == 0: zero state, unet.py:23-25), slot t+1 = h_t; c_all: fp32 [T+1][...] likewise;
+ * gates: bf16 [T][P][4][Ch] activated i,f,g,o (kept for BPTT).  Also uses one 4-byte per-device step
+ * counter owned by the library. */
+int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all, int Ch, int T, int B, int H, int W,
+                             const void* wpacked, const float* bias_packed, float* c_all, void* gates,
+                             int have_h0, int ksize, void* stream);
+
 /* Weight gradient of a convolution, summed over all T*B images (autograd of nn.Conv2d, unet.py:19
  * and :70-71; for the ConvLSTM this is the BPTT sum over timesteps):
  *   dw[tap][n][koff + k] += sum_{t,p} dz[t,p,n] * src[t, p+tap, k]

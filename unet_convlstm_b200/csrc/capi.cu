@@ -77,6 +77,29 @@ extern "C" int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_p
     return launch_conv_tc(x, h_prev, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all, int Ch, int T, int B, int H, int W,
+                                        const void* wpacked, const float* bias_packed, float* c_all, void* gates,
+                                        int have_h0, int ksize, void* stream) {
+    if (!x_seq || !h_all || !wpacked || !c_all || !gates || Ch <= 0 || Cin <= 0 || T <= 0) {
+        set_last_error("b200_convlstm_seq_fwd_tc: bad arguments");
+        return B200_ERR_ARG;
+    }
+    const long long slot = static_cast<long long>(B) * H * W * Ch;
+    ConvTcParams p = {};
+    p.T = 1; p.B = B; p.H = H; p.W = W;
+    p.C0 = Cin; p.C1 = Ch;
+    p.N = 4 * Ch; p.ksize = ksize;
+    p.wK = Cin + Ch;
+    p.bias = bias_packed;
+    p.c_prev = c_all;
+    p.c_next = c_all + slot;
+    p.h_next = static_cast<__nv_bfloat16*>(h_all) + slot;
+    p.gates_out = static_cast<__nv_bfloat16*>(gates);
+    p.seq_T = T;
+    p.seq_have_h0 = have_h0;
+    return launch_convlstm_seq_tc(x_seq, h_all, wpacked, p, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
                              int ksize, float* dw, long long ldk, int koff, void* stream) {
     if (!dz || !src || !dw || Nz <= 0 || Csrc <= 0 || (ksize & 1) == 0 || koff < 0 || koff + Csrc > ldk) {

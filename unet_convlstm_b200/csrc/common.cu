@@ -46,6 +46,21 @@ int* device_error_flag() {
     return flags[dev];
 }
 
+unsigned* device_sync_counter() {
+    static unsigned* ctrs[64] = {nullptr};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!ctrs[dev]) {
+        unsigned* p = nullptr;
+        if (cudaMalloc(&p, sizeof(unsigned)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, sizeof(unsigned));
+        ctrs[dev] = p;
+    }
+    return ctrs[dev];
+}
+
 // ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

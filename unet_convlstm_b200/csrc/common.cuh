@@ -30,6 +30,7 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();
 int* device_error_flag();  // one int in device memory, zero unless a watchdog fired
+unsigned* device_sync_counter();  // one step counter per device for the timestep-persistent kernels
 
 // ---- TMA tensor-map construction (driver entry point resolved at run time, no libcuda link) ----
 // Activation map over a bf16 NHWC tensor viewed as {C, W, H, B, T}; box = {box_c, Wt, Ht, Bt, 1}.

@@ -47,6 +47,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Spin (bounded) until the grid-wide step counter reaches `target`.  Safe only under a cooperative
+// launch, where every CTA of the grid is resident.
+__device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, int* err_flag) {
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        if (clock64() - t0 > 8000000000LL) {
+            if (err_flag) atomicExch(err_flag, 900);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    } while (true);
+}
+
 struct TileCoord {
     int n0, t, b0, h0, w0;
 };
@@ -96,6 +112,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     const int chunks = chunks0 + chunks1;
     const int num_kb = taps * chunks;
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    // timestep-persistent mode (EPI_LSTM only): the kernel iterates over the whole sequence, h_t and
+    // c_t stay in the L2-resident state buffers and a grid-wide counter separates the steps
+    const bool seq = p.seq_T > 0;
+    const int nsteps = seq ? p.seq_T : 1;
     const uint32_t a_bytes = BLOCK_M * p.kc * 2;
     const uint32_t b_bytes = BLOCK_N * p.kc * 2;
 
@@ -135,13 +155,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             uint32_t phase = 0;
             uint32_t a_dst = smem_base;
             const uint32_t tx_bytes = a_bytes + b_bytes;
+            for (int step = 0; step < nsteps; ++step) {
+            const int chunks_t = (seq && step == 0 && !p.seq_have_h0) ? chunks0 : chunks;
+            if (seq && step > 0) {
+                // h_{t-1} was written by the epilogue warps of every CTA in the previous step
+                grid_wait(p.sync_ctr, gridDim.x * step, p.err_flag);
+                fence_proxy_async_all();
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(p, tile, BLOCK_N);
+                TileCoord tc = decode_tile(p, tile, BLOCK_N);
+                if (seq) tc.t = step;
                 int ky = 0, kx = 0;
                 for (int tap = 0; tap < taps; ++tap) {
                     const int cw = tc.w0 + kx - p.pad, chh = tc.h0 + ky - p.pad;
                     int kofs = 0;
-                    for (int c = 0; c < chunks; ++c, kofs += p.kc) {
+                    for (int c = 0; c < chunks_t; ++c, kofs += p.kc) {
                         mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
                         const uint32_t fb = full_bar(stage);
                         mbar_arrive_expect_tx(fb, tx_bytes);
@@ -163,6 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
@@ -182,12 +211,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             uint32_t a_lo = (smem_base & 0x3FFFFu) >> 4;
             const uint32_t a_lo0 = a_lo;
             constexpr uint32_t STAGE_LO = Cfg::STAGE_BYTES >> 4, B_LO = Cfg::A_BYTES >> 4;
+            for (int step = 0; step < nsteps; ++step) {
+            const int num_kb_t = (seq && step == 0 && !p.seq_have_h0) ? taps * chunks0 : num_kb;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 uint32_t accum = 0;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = 0; kb < num_kb_t; ++kb) {
                     mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
                     tc_fence_after();
                     const uint64_t adesc = desc_hi | a_lo;
@@ -218,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     acc_phase ^= 1u;
                 }
             }
+            }
         }
     } else if (warp >= EPI_WARP0) {
         // =================================== epilogue =======================================
@@ -228,8 +260,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         const int bi = r / (p.Wt * p.Ht);
         int acc = 0;
         uint32_t acc_phase = 0;
+        for (int step = 0; step < nsteps; ++step) {
+        const bool zero_state = seq && step == 0 && !p.seq_have_h0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(p, tile, BLOCK_N);
+            TileCoord tc = decode_tile(p, tile, BLOCK_N);
+            if (seq) tc.t = step;
             const bool valid = (tc.h0 + hi < p.H) && (tc.b0 + bi < p.B);
             const long long pix =
                 ((static_cast<long long>(tc.t) * p.B + tc.b0 + bi) * p.H + tc.h0 + hi) * p.W + tc.w0 + wi;
@@ -300,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                         const int ch = ch0 + j0;
                         const long long coff = pix * Ch + ch;
                         float cp[16];
-                        if (p.c_prev) {
+                        if (p.c_prev && !zero_state) {
                             const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + coff);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -370,6 +405,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 acc_phase ^= 1u;
             }
         }
+        if (seq && step + 1 < nsteps) {
+            // publish h_t / c_t of this CTA's tiles, then signal the grid-wide step counter
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == EPI_WARP0 * 32) {
+                __threadfence();
+                atomicAdd(p.sync_ctr, 1u);
+            }
+        }
+        }
     }
 
     // ---- teardown ----
@@ -409,9 +453,28 @@ static int launch_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
     }
     int total = p.num_m_tiles * p.num_n_tiles;
     int grid = total < num_sms() ? total : num_sms();
+    if (p.seq_T > 0) {
+        // the steps are separated by a grid-wide counter: every CTA must be resident -> cooperative launch
+        B200_CUDA_CHECK(cudaMemsetAsync(p.sync_ctr, 0, sizeof(unsigned), stream));
+        void* args[] = {const_cast<CUtensorMap*>(&ta0), const_cast<CUtensorMap*>(&ta1),
+                        const_cast<CUtensorMap*>(&tb), const_cast<ConvTcParams*>(&p)};
+        B200_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid),
+                                                    dim3(NUM_THREADS), args, Cfg::SMEM_BYTES, stream));
+        return B200_OK;
+    }
     kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta0, ta1, tb, p);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200_OK;
+}
+
+int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpacked, ConvTcParams p,
+                           cudaStream_t stream) {
+    p.sync_ctr = device_sync_counter();
+    if (!p.sync_ctr || p.seq_T <= 0) {
+        set_last_error("convlstm_seq_tc: no step counter / bad sequence length");
+        return B200_ERR_ARG;
+    }
+    return launch_conv_tc(x_seq, h_all, wpacked, p, EPI_LSTM, stream);
 }
 
 int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi,
@@ -444,16 +507,18 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
     p.tiles_w = mt.tiles_w;
     p.tiles_h = mt.tiles_h;
     p.tiles_b = mt.tiles_b;
+    const int map_T = p.seq_T > 0 ? p.seq_T : p.T;
+    if (p.seq_T > 0) p.T = 1;  // tiles of ONE step; the kernel iterates over the steps itself
     p.num_m_tiles = p.T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
     p.num_n_tiles = (p.N + block_n - 1) / block_n;
     p.pad = p.ksize / 2;
     p.err_flag = device_error_flag();
 
     CUtensorMap ta0, ta1, tb;
-    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, p.T, kc, mt.Wt, mt.Ht, mt.Bt);
+    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
     if (p.C1 > 0) {
-        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, p.T, kc, mt.Wt, mt.Ht, mt.Bt);
+        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt);
         if (rc != B200_OK) return rc;
     } else {
         ta1 = ta0;

@@ -35,12 +35,22 @@ struct ConvTcParams {
     float* c_next;              // [P, Ch] fp32
     __nv_bfloat16* h_next;      // [P, Ch] bf16
     __nv_bfloat16* gates_out;   // [P, 4, Ch] bf16 post-activation i,f,g,o or nullptr
+    // timestep-persistent mode (EPI_LSTM): seq_T > 0 -> the kernel loops over seq_T steps; source 0 is
+    // x_seq [T], source 1 is h_all [T+1] (slot t = h_{t-1}), c_prev/c_next/h_next/gates_out point at
+    // slot 0 / slot 1 / slot 1 / step 0 of their sequence buffers
+    int seq_T;
+    int seq_have_h0;
+    unsigned* sync_ctr;
     int* err_flag;
 };
 
 // Launches the kernel for one problem.  All pointers are device pointers; maps are built per call.
 int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi,
                    cudaStream_t stream);
+
+// Whole-sequence forward of one ConvLSTM layer in ONE cooperative launch (see ConvTcParams::seq_T).
+int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpacked, ConvTcParams p,
+                           cudaStream_t stream);
 
 // Picks BLOCK_N for a given GEMM N (multiple of 16).  LSTM epilogue needs N % 64 == 0.
 int pick_block_n(int N, int epi);

@@ -250,10 +250,14 @@ class ConvLSTMSeq(torch.autograd.Function):
             h_all[0].zero_()
         if fused:
             wp, bp = cache.get(("lstm", dt), (weight, bias), lambda: ops.pack_lstm_weight(weight, bias, dt))
-            for t in range(T):
-                first_zero = (t == 0 and not have_h0)
-                ops.lstm_cell_fwd_fused(x_seq[t], None if first_zero else h_all[t], None if first_zero else c_all[t],
-                                        wp, bp, c_all[t + 1], h_all[t + 1], gates[t], ks)
+            if ops.PERSISTENT_LSTM:
+                ops.lstm_seq_fwd_fused(x_seq, h_all, c_all, wp, bp, gates, have_h0, ks)
+            else:
+                for t in range(T):
+                    first_zero = (t == 0 and not have_h0)
+                    ops.lstm_cell_fwd_fused(x_seq[t], None if first_zero else h_all[t],
+                                            None if first_zero else c_all[t], wp, bp, c_all[t + 1], h_all[t + 1],
+                                            gates[t], ks)
         else:
             wp = cache.get(("fwd", dt, Cin + Ch), (weight,), lambda: ops.pack_conv_weight(weight, dt))
             zbuf = torch.empty((B, H, W, 4 * Ch), device=dev, dtype=torch.float32)

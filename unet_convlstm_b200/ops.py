@@ -360,6 +360,9 @@ def lstm_tc_ok(x_t, Ch) -> bool:
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
 
+# One cooperative timestep-persistent launch per ConvLSTM layer (default) or one launch per timestep
+PERSISTENT_LSTM = os.environ.get("B200_PERSISTENT_LSTM", "1") != "0"
+
 # bench.py sets this to a list to time every fused cell launch with CUDA events on the launching stream:
 # entries are (start_event, end_event, algorithmic_flops)
 CELL_TIMER = None
@@ -382,6 +385,24 @@ def lstm_cell_fwd_fused(x_t, h_prev, c_prev, wp_il, bias_il, c_next, h_next, gat
         e1.record()
         kin = Cin + (Ch if h_prev is not None else 0)
         timer.append((e0, e1, 2.0 * B * H * W * ksize * ksize * kin * 4 * Ch))
+
+
+def lstm_seq_fwd_fused(x_seq, h_all, c_all, wp_il, bias_il, gates, have_h0, ksize):
+    """All T steps of one ConvLSTM layer in one timestep-persistent cooperative launch."""
+    T, B, H, W, Cin = x_seq.shape
+    Ch = c_all.shape[-1]
+    kin = Cin + Ch
+    fl = 2.0 * B * H * W * ksize * ksize * 4 * Ch * (kin * T - (0 if have_h0 else Ch))
+    timer = CELL_TIMER
+    if timer is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.call("b200_convlstm_seq_fwd_tc", _p(x_seq), Cin, _p(h_all), Ch, T, B, H, W, _p(wp_il), _p(bias_il),
+              _p(c_all), _p(gates), int(have_h0), ksize, _st(), tag=f"Ch{Ch} {H}x{W} T{T}", work=(fl, None))
+    if timer is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        timer.append((e0, e1, fl))
 
 
 def lstm_cell_fwd_unfused(x_t, h_prev, c_prev, wp, bias, c_next, h_next, gates, ksize, zbuf):
