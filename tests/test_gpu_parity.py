@@ -316,7 +316,13 @@ def _simt_conv(x0, x1, wp, bias, ks, n_out):
 @pytest.mark.parametrize("T,B,H,W,C0,C1,N,ks", [(2, 3, 8, 8, 64, 64, 256, 3), (1, 2, 32, 32, 64, 128, 192, 3),
                                                 (1, 2, 16, 16, 32, 32, 96, 3), (2, 4, 4, 4, 128, 0, 256, 3),
                                                 (1, 1, 16, 128, 64, 0, 128, 3), (1, 2, 16, 16, 16, 0, 32, 1),
-                                                (1, 2, 64, 64, 16, 0, 64, 3), (1, 1, 12, 16, 64, 0, 64, 3)])
+                                                (1, 2, 64, 64, 16, 0, 64, 3), (1, 1, 12, 16, 64, 0, 64, 3),
+                                                # narrow layers: the halo kernel (conv_halo.cu), resident and
+                                                # streamed weights, one and two sources, odd heights
+                                                (2, 4, 64, 64, 64, 0, 64, 3), (1, 4, 64, 64, 64, 64, 64, 3),
+                                                (1, 4, 32, 32, 128, 0, 128, 3), (1, 2, 32, 32, 128, 128, 128, 3),
+                                                (1, 3, 16, 16, 64, 0, 128, 3), (1, 2, 7, 16, 64, 0, 48, 3),
+                                                (1, 2, 64, 64, 128, 0, 64, 3)])
 def test_conv_tc_vs_simt(T, B, H, W, C0, C1, N, ks):
     from unet_convlstm_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(1)

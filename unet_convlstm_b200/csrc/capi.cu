@@ -5,6 +5,8 @@
 #include "conv_tc.cuh"
 #include "pointwise.cuh"
 
+#include <stdlib.h>
+
 using namespace b200;
 
 namespace b200 {
@@ -47,6 +49,17 @@ extern "C" int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int 
         set_last_error("b200_conv_tc_fwd: accumulate requires fp32 output");
         return B200_ERR_ARG;
     }
+    // narrow layers are bound by the L2 -> smem fill rate of the per-tap activation boxes: use the halo
+    // kernel (activation tile loaded once per output tile).  B200_CONV_HALO=0 disables, =2 forces it
+    // for every shape it supports.
+    static const int halo_mode = [] {
+        const char* e = getenv("B200_CONV_HALO");
+        return e ? atoi(e) : 1;
+    }();
+    if (halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
+        conv_halo_supported(T * B, H, W, C0, C1, N, ksize))
+        return launch_conv_halo(src0, src1, wpacked, T * B, H, W, C0, C1, N, bias, dst0, ld0, split, dst1, ld1,
+                                out_fp32, relu, accumulate, static_cast<cudaStream_t>(stream));
     ConvTcParams p = {};
     p.T = T; p.B = B; p.H = H; p.W = W;
     p.C0 = C0; p.C1 = C1; p.N = N; p.ksize = ksize;

@@ -52,6 +52,12 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
 int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpacked, ConvTcParams p,
                            cudaStream_t stream);
 
+// conv_halo.cu: 3x3 convolution with the activation tile loaded once per output tile (narrow layers).
+bool conv_halo_supported(int IMG, int H, int W, int C0, int C1, int N, int ksize);
+int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, int IMG, int H, int W, int C0, int C1,
+                     int N, const float* bias, void* dst0, long long ld0, int split, void* dst1, long long ld1,
+                     int out_fp32, int relu, int accumulate, cudaStream_t stream);
+
 // Picks BLOCK_N for a given GEMM N (multiple of 16).  LSTM epilogue needs N % 64 == 0.
 int pick_block_n(int N, int epi);
 
