@@ -120,40 +120,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
-        if (lane == 0) {
-            if (p.wres) {
-                // resident weights: all (tap, chunk) boxes of N tile 0, once
+        // The whole warp runs the loop converged and ONE elected lane issues (elect.sync): ptxas then
+        // emits straight-line UTMALDG code instead of the per-instruction ELECT/branch loop it needs
+        // under a divergent `lane == 0` guard.
+        if (p.wres) {
+            // resident weights: all (tap, chunk) boxes of N tile 0, once
+            if (elect_one()) {
                 mbar_arrive_expect_tx(wfull, 9u * p.chunks * p.b_box_bytes);
                 uint32_t dst = b_base;
                 for (int tap = 0; tap < 9; ++tap)
                     for (int c = 0; c < p.chunks; ++c, dst += p.b_box_bytes) tma_load_3d(dst, &tm_b, wfull, c * 64, 0, tap);
             }
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int n0, img, q0, r0;
-                decode(tile, n0, img, q0, r0);
-                for (int c = 0; c < p.chunks; ++c) {
-                    mbar_wait(aempty(sa), pa ^ 1u, p.err_flag, 100 + sa);
+            __syncwarp();
+        }
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int n0, img, q0, r0;
+            decode(tile, n0, img, q0, r0);
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(aempty(sa), pa ^ 1u, p.err_flag, 100 + sa);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(afull(sa), p.a_box_bytes);
                     const uint32_t dst = a_base + sa * p.a_stage_bytes;
                     if (c < p.chunks0)
                         tma_load_5d(dst, &tm_a0, afull(sa), c * 64, -1, r0 - 1, img, 0);
                     else
                         tma_load_5d(dst, &tm_a1, afull(sa), (c - p.chunks0) * 64, -1, r0 - 1, img, 0);
-                    if (++sa == p.SA) {
-                        sa = 0;
-                        pa ^= 1u;
-                    }
-                    if (!p.wres) {
-                        for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(bempty(sb), pb ^ 1u, p.err_flag, 120 + sb);
+                }
+                __syncwarp();
+                if (++sa == p.SA) {
+                    sa = 0;
+                    pa ^= 1u;
+                }
+                if (!p.wres) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(bempty(sb), pb ^ 1u, p.err_flag, 120 + sb);
+                        if (elect_one()) {
                             mbar_arrive_expect_tx(bfull(sb), p.b_box_bytes);
                             tma_load_3d(b_base + sb * p.b_box_bytes, &tm_b, bfull(sb), c * 64, n0, tap);
-                            if (++sb == p.SB) {
-                                sb = 0;
-                                pb ^= 1u;
-                            }
+                        }
+                        __syncwarp();
+                        if (++sb == p.SB) {
+                            sb = 0;
+                            pb ^= 1u;
                         }
                     }
                 }
@@ -161,68 +171,88 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         }
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(H_BLOCK_M, BLOCK_N, 0, 0);
-            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);  // K-major, 128 B rows, 128B swizzle
-            const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4, b_lo0 = (b_base & 0x3FFFFu) >> 4;
-            const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_box_lo = p.b_box_bytes >> 4;
-            const uint32_t row_lo = 128u >> 4;  // one padded position = one 128-byte row
-            if (p.wres) {
-                mbar_wait(wfull, 0, p.err_flag, 250);
+        // converged warp, one elected lane issues (see the producer): back-to-back UTCHMMA
+        const uint32_t idesc = make_idesc_bf16(H_BLOCK_M, BLOCK_N, 0, 0);
+        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);  // K-major, 128 B rows, 128B swizzle
+        const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4, b_lo0 = (b_base & 0x3FFFFu) >> 4;
+        const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_box_lo = p.b_box_bytes >> 4;
+        const uint32_t row_lo = 128u >> 4;  // one padded position = one 128-byte row
+        if (p.wres) {
+            mbar_wait(wfull, 0, p.err_flag, 250);
+            tc_fence_after();
+        }
+        int sa = 0, sb = 0, acc = 0;
+        uint32_t pa = 0, pb = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int n0, img, q0, r0;
+            decode(tile, n0, img, q0, r0);
+            const uint32_t off = q0 - r0 * p.P;  // first output position inside the loaded box
+            mbar_wait(tempty(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t accum = 0;
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(afull(sa), pa, p.err_flag, 200 + sa);
                 tc_fence_after();
-            }
-            int sa = 0, sb = 0, acc = 0;
-            uint32_t pa = 0, pb = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int n0, img, q0, r0;
-                decode(tile, n0, img, q0, r0);
-                const uint32_t off = q0 - r0 * p.P;  // first output position inside the loaded box
-                mbar_wait(tempty(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                uint32_t accum = 0;
-                for (int c = 0; c < p.chunks; ++c) {
-                    mbar_wait(afull(sa), pa, p.err_flag, 200 + sa);
-                    tc_fence_after();
-                    uint32_t a_row = a_lo0 + sa * a_stage_lo + off * row_lo;  // tap (0, 0)
-                    int tap = 0;
-                    for (int ky = 0; ky < 3; ++ky, a_row += (p.P - 3) * row_lo) {
-                        for (int kx = 0; kx < 3; ++kx, ++tap, a_row += row_lo) {
-                            uint32_t b_lo;
-                            if (p.wres) {
-                                b_lo = b_lo0 + (tap * p.chunks + c) * b_box_lo;
-                            } else {
-                                mbar_wait(bfull(sb), pb, p.err_flag, 220 + sb);
-                                tc_fence_after();
-                                b_lo = b_lo0 + sb * b_box_lo;
+                const uint32_t a_row0 = a_lo0 + sa * a_stage_lo + off * row_lo;  // tap (0, 0)
+                if (p.wres) {
+                    if (elect_one()) {
+                        uint32_t a_row = a_row0;
+                        uint32_t b_lo = b_lo0 + c * b_box_lo;
+                        const uint32_t b_tap_lo = p.chunks * b_box_lo;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky, a_row += (p.P - 3) * row_lo) {
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx, a_row += row_lo, b_lo += b_tap_lo) {
+                                const uint64_t adesc = desc_hi | a_row;
+                                const uint64_t bdesc = desc_hi | b_lo;
+                                umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                                accum = 1u;
                             }
-                            const uint64_t adesc = desc_hi | a_row;
-                            const uint64_t bdesc = desc_hi | b_lo;
-                            umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                            umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                            umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                            umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-                            accum = 1u;
-                            if (!p.wres) {
+                        }
+                        umma_commit(aempty(sa));  // every tap of this chunk has read the activation box
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                } else {
+                    uint32_t a_row = a_row0;
+                    for (int ky = 0; ky < 3; ++ky, a_row += (p.P - 3) * row_lo) {
+                        for (int kx = 0; kx < 3; ++kx, a_row += row_lo) {
+                            mbar_wait(bfull(sb), pb, p.err_flag, 220 + sb);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t adesc = desc_hi | a_row;
+                                const uint64_t bdesc = desc_hi | (b_lo0 + sb * b_box_lo);
+                                umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
                                 umma_commit(bempty(sb));
-                                if (++sb == p.SB) {
-                                    sb = 0;
-                                    pb ^= 1u;
-                                }
+                            }
+                            __syncwarp();
+                            accum = 1u;
+                            if (++sb == p.SB) {
+                                sb = 0;
+                                pb ^= 1u;
                             }
                         }
                     }
-                    umma_commit(aempty(sa));  // every tap of this chunk has read the activation box
-                    if (++sa == p.SA) {
-                        sa = 0;
-                        pa ^= 1u;
-                    }
+                    if (elect_one()) umma_commit(aempty(sa));
+                    __syncwarp();
                 }
-                umma_commit(tfull(acc));
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                if (++sa == p.SA) {
+                    sa = 0;
+                    pa ^= 1u;
                 }
+            }
+            if (elect_one()) umma_commit(tfull(acc));
+            __syncwarp();
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
             }
         }
     } else if (warp >= 4) {

@@ -146,21 +146,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
-        // One thread issues every copy, so the loop body is kept to a handful of instructions: the
-        // (tap, channel-chunk) index is carried by nested counters, never derived by division
-        // (with N = 64 tiles a K block is only 128 tensor-pipe cycles and a heavier producer loop
-        // becomes the bottleneck: profiles/r01_ncu_wgrad_stacked_issue_bound.txt).
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t a_dst = smem_base;
-            const uint32_t tx_bytes = a_bytes + b_bytes;
-            for (int step = 0; step < nsteps; ++step) {
+        // The whole warp runs the loop converged and ONE elected lane (elect.sync) issues the copies:
+        // ptxas then emits straight-line UTMALDG code; under a divergent `lane == 0` guard it wraps
+        // every copy in an ELECT / branch loop, which made the N = 64 tiles (a K block is only 128
+        // tensor-pipe cycles) issue-bound (profiles/r01_ncu_conv_halo_issue_loop.txt).  The (tap,
+        // channel-chunk) index is carried by nested counters, never derived by division.
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t a_dst = smem_base;
+        const uint32_t tx_bytes = a_bytes + b_bytes;
+        for (int step = 0; step < nsteps; ++step) {
             const int chunks_t = (seq && step == 0 && !p.seq_have_h0) ? chunks0 : chunks;
             if (seq && step > 0) {
                 // h_{t-1} was written by the epilogue warps of every CTA in the previous step
-                grid_wait(p.sync_ctr, gridDim.x * step, p.err_flag);
-                fence_proxy_async_all();
+                if (lane == 0) grid_wait(p.sync_ctr, gridDim.x * step, p.err_flag);
+                __syncwarp();
+                fence_proxy_async_all();  // every lane: whichever one is elected issues the TMA reads
             }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 TileCoord tc = decode_tile(p, tile, BLOCK_N);
@@ -171,13 +172,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     int kofs = 0;
                     for (int c = 0; c < chunks_t; ++c, kofs += p.kc) {
                         mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
-                        const uint32_t fb = full_bar(stage);
-                        mbar_arrive_expect_tx(fb, tx_bytes);
-                        if (c < chunks0)
-                            tma_load_5d(a_dst, &tm_a0, fb, kofs, cw, chh, tc.b0, tc.t);
-                        else
-                            tma_load_5d(a_dst, &tm_a1, fb, kofs - p.C0, cw, chh, tc.b0, tc.t);
-                        tma_load_3d(a_dst + Cfg::A_BYTES, &tm_b, fb, kofs, tc.n0, tap);
+                        if (elect_one()) {
+                            const uint32_t fb = full_bar(stage);
+                            mbar_arrive_expect_tx(fb, tx_bytes);
+                            if (c < chunks0)
+                                tma_load_5d(a_dst, &tm_a0, fb, kofs, cw, chh, tc.b0, tc.t);
+                            else
+                                tma_load_5d(a_dst, &tm_a1, fb, kofs - p.C0, cw, chh, tc.b0, tc.t);
+                            tma_load_3d(a_dst + Cfg::A_BYTES, &tm_b, fb, kofs, tc.n0, tap);
+                        }
+                        __syncwarp();
                         a_dst += Cfg::STAGE_BYTES;
                         if (++stage == STAGES) {
                             stage = 0;
@@ -191,27 +195,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     }
                 }
             }
-            }
         }
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-            // K-major swizzled operand tiles: rows of kc*2 bytes, 8-row atoms => SBO = 8 * row bytes
-            const uint32_t row_bytes = p.kc * 2;
-            const uint32_t layout_type = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
-            const uint32_t sbo = 8u * row_bytes;
-            const int mma_per_kb = p.kc / 16;
-            // descriptor = constant high part | (smem address >> 4); only the address changes per stage
-            const uint64_t desc_hi = make_smem_desc(0, 16, sbo, layout_type);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            uint32_t a_lo = (smem_base & 0x3FFFFu) >> 4;
-            const uint32_t a_lo0 = a_lo;
-            constexpr uint32_t STAGE_LO = Cfg::STAGE_BYTES >> 4, B_LO = Cfg::A_BYTES >> 4;
-            for (int step = 0; step < nsteps; ++step) {
+        // converged warp, one elected lane issues (see the producer): back-to-back UTCHMMA
+        const uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        // K-major swizzled operand tiles: rows of kc*2 bytes, 8-row atoms => SBO = 8 * row bytes
+        const uint32_t row_bytes = p.kc * 2;
+        const uint32_t layout_type = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
+        const uint32_t sbo = 8u * row_bytes;
+        const int mma_per_kb = p.kc / 16;
+        // descriptor = constant high part | (smem address >> 4); only the address changes per stage
+        const uint64_t desc_hi = make_smem_desc(0, 16, sbo, layout_type);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t a_lo = (smem_base & 0x3FFFFu) >> 4;
+        const uint32_t a_lo0 = a_lo;
+        constexpr uint32_t STAGE_LO = Cfg::STAGE_BYTES >> 4, B_LO = Cfg::A_BYTES >> 4;
+        for (int step = 0; step < nsteps; ++step) {
             const int num_kb_t = (seq && step == 0 && !p.seq_have_h0) ? taps * chunks0 : num_kb;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
@@ -221,21 +224,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 for (int kb = 0; kb < num_kb_t; ++kb) {
                     mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
                     tc_fence_after();
-                    const uint64_t adesc = desc_hi | a_lo;
-                    const uint64_t bdesc = desc_hi | (a_lo + B_LO);
-                    if (mma_per_kb == 4) {
-                        // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in >>4 units
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                        umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                        umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                        umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-                    } else {
-                        for (int k = 0; k < mma_per_kb; ++k)
-                            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
-                                      k == 0 ? accum : 1u);
+                    if (elect_one()) {
+                        const uint64_t adesc = desc_hi | a_lo;
+                        const uint64_t bdesc = desc_hi | (a_lo + B_LO);
+                        if (mma_per_kb == 4) {
+                            // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in >>4 units
+                            umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                            umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                            umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                            umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                        } else {
+                            for (int k = 0; k < mma_per_kb; ++k)
+                                umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                                          k == 0 ? accum : 1u);
+                        }
+                        umma_commit(empty_bar(stage));  // frees the smem slot when the MMAs retire
                     }
+                    __syncwarp();
                     accum = 1u;
-                    umma_commit(empty_bar(stage));  // frees the smem slot when the MMAs retire
                     a_lo += STAGE_LO;
                     if (++stage == STAGES) {
                         stage = 0;
@@ -243,12 +249,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                         a_lo = a_lo0;
                     }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                __syncwarp();
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1u;
                 }
-            }
             }
         }
     } else if (warp >= EPI_WARP0) {

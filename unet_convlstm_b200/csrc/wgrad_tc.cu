@@ -170,10 +170,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
-        // The whole warp takes part: lane l owns one (tap group, box) pair of the varying operand --
-        // its tap shift is fixed for the unit -- and lanes 0..boxesS-1 the dz boxes, so the per-block
-        // work of each lane is a few adds and one copy; the pixel-block coordinates are carried by
-        // nested counters (no divisions in the loop).
+        // The warp runs converged and ONE elected lane (elect.sync) issues every copy -- straight-line
+        // UTMALDG code; a divergent per-lane issue makes ptxas wrap each copy in an ELECT/branch loop.
+        // Lane l still PRECOMPUTES the tap shift and channel offset of "its" (tap group, box) pair of
+        // the varying operand once per unit; the elected lane fetches them with a shuffle, so the
+        // per-block work is a few adds per copy; the pixel-block coordinates are carried by nested
+        // counters (no divisions in the loop).
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -182,22 +184,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             const int boxesV = STACKED ? p.G : (u.vcols + cwV - 1) / cwV;
             const int rb_begin = u.split * p.rb_per_split;
             const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-            // this lane's varying box: group my_g, box my_i
+            // this lane's varying box: group my_g, box my_i -> packed (dx, dy, channel offset)
             const int my_g = lane / boxesV, my_i = lane - my_g * boxesV;
-            const bool v_lane = my_g < u.ngr;
-            int my_dx = 0, my_dy = 0, my_c = 0;
-            if (v_lane) {
+            int my_pack = 0;
+            if (my_g < u.ngr) {
                 const int grp = u.gset * p.GU + my_g;
                 // stacked: taps beyond the filter repeat the last one; their rows are never stored
                 const int tp = STACKED ? min(grp * p.G + my_i, p.taps - 1) : grp;
                 const int sy = tp / p.ksize;
-                my_dy = sy - p.pad;
-                my_dx = tp - sy * p.ksize - p.pad;
-                my_c = STACKED ? 0 : u.v0 + my_i * cwV;
+                const int dy = sy - p.pad, dx = tp - sy * p.ksize - p.pad;
+                const int c = STACKED ? 0 : u.v0 + my_i * cwV;
+                my_pack = (c << 8) | ((dy + 8) << 4) | (dx + 8);
             }
-            const uint32_t my_voff = my_i * boxV_bytes;
-            const bool s_lane = lane < boxesS;
-            const int my_sc = u.s0 + lane * cwS;
             const uint32_t s_tx = boxesS * boxS_bytes, v_tx = boxesV * boxV_bytes;
             // pixel-block counters
             int m = rb_begin;
@@ -210,27 +208,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             for (int rb = rb_begin; rb < rb_end; ++rb) {
                 const int w0 = wt * p.Wt, h0 = ht * p.Ht, b0 = bt * p.Bt;
                 // shared operand: the dz box(es) of this pixel block
-                if (lane == 0) {
-                    mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 500 + ss);
+                mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 500 + ss);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(sfull(ss), s_tx);
+                    uint32_t dst = s_base + ss * Cfg::S_BYTES;
+                    int sc = u.s0;
+                    for (int i = 0; i < boxesS; ++i, dst += boxS_bytes, sc += cwS)
+                        tma_load_5d(dst, &tm_dz, sfull(ss), sc, w0, h0, b0, t);
                 }
                 __syncwarp();
-                if (s_lane)
-                    tma_load_5d(s_base + ss * Cfg::S_BYTES + lane * boxS_bytes, &tm_dz, sfull(ss), my_sc, w0, h0, b0, t);
                 if (++ss == SS) {
                     ss = 0;
                     ps ^= 1u;
                 }
                 // varying operand: one stage per tap group
+                int src_lane = 0;
                 for (int g = 0; g < u.ngr; ++g) {
-                    if (lane == 0) {
-                        mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
-                        mbar_arrive_expect_tx(vfull(sv), v_tx);
+                    mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
+                    uint32_t dst = v_base + sv * Cfg::V_BYTES;
+                    if (elect_one()) mbar_arrive_expect_tx(vfull(sv), v_tx);
+                    for (int i = 0; i < boxesV; ++i, ++src_lane, dst += boxV_bytes) {
+                        const int pk = __shfl_sync(0xffffffffu, my_pack, src_lane);
+                        if (elect_one())
+                            tma_load_5d(dst, &tm_src, vfull(sv), pk >> 8, w0 + (pk & 15) - 8, h0 + ((pk >> 4) & 15) - 8,
+                                        b0, t);
                     }
                     __syncwarp();
-                    if (v_lane && my_g == g)
-                        tma_load_5d(v_base + sv * Cfg::V_BYTES + my_voff, &tm_src, vfull(sv), my_c, w0 + my_dx,
-                                    h0 + my_dy, b0, t);
                     if (++sv == SV) {
                         sv = 0;
                         pv ^= 1u;
@@ -250,34 +253,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         }
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
-        if (lane == 0) {
-            const uint32_t ltA = (cwA == 64) ? 2u : (cwA == 32 ? 4u : 6u);
-            const uint32_t ltB = (cwB == 64) ? 2u : (cwB == 32 ? 4u : 6u);
-            // descriptor = constant high part | (smem address >> 4); 16 pixels (one MMA K step) further
-            // down the box = two 8-row atoms = 16 * cw * 2 bytes
-            const uint64_t hiA = make_smem_desc(0, boxA_bytes, 8u * cwA * 2, ltA);
-            const uint64_t hiB = make_smem_desc(0, boxB_bytes, 8u * cwB * 2, ltB);
-            const uint32_t stepA = (16u * cwA * 2) >> 4, stepB = (16u * cwB * 2) >> 4;
-            const uint32_t v_lo0 = (v_base & 0x3FFFFu) >> 4, s_lo0 = (s_base & 0x3FFFFu) >> 4;
-            int sv = 0, ss = 0;
-            uint32_t pv = 0, ps = 0, pt = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-                const WgUnit u = wg_decode<BLOCK_N, STACKED>(p, unit);
-                const int ncols = STACKED ? u.scols : u.vcols;
-                const int nmma = ((ncols + cwB - 1) / cwB) * cwB;  // whole loaded boxes
-                const uint32_t idesc = make_idesc_bf16(WG_BLOCK_M, nmma, 1, 1);
-                const int rb_begin = u.split * p.rb_per_split;
-                const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-                mbar_wait(tempty, pt ^ 1u, p.err_flag, 700);
-                tc_fence_after();
-                uint32_t accum = 0;
-                for (int rb = rb_begin; rb < rb_end; ++rb) {
-                    mbar_wait(sfull(ss), ps, p.err_flag, 600 + ss);
-                    const uint32_t s_lo = s_lo0 + ss * (Cfg::S_BYTES >> 4);
-                    uint32_t d_tmem = tmem_base;
-                    for (int g = 0; g < u.ngr; ++g, d_tmem += BLOCK_N) {
-                        mbar_wait(vfull(sv), pv, p.err_flag, 620 + sv);
-                        tc_fence_after();
+        // converged warp, one elected lane issues (see the producer): back-to-back UTCHMMA
+        const uint32_t ltA = (cwA == 64) ? 2u : (cwA == 32 ? 4u : 6u);
+        const uint32_t ltB = (cwB == 64) ? 2u : (cwB == 32 ? 4u : 6u);
+        // descriptor = constant high part | (smem address >> 4); 16 pixels (one MMA K step) further
+        // down the box = two 8-row atoms = 16 * cw * 2 bytes
+        const uint64_t hiA = make_smem_desc(0, boxA_bytes, 8u * cwA * 2, ltA);
+        const uint64_t hiB = make_smem_desc(0, boxB_bytes, 8u * cwB * 2, ltB);
+        const uint32_t stepA = (16u * cwA * 2) >> 4, stepB = (16u * cwB * 2) >> 4;
+        const uint32_t v_lo0 = (v_base & 0x3FFFFu) >> 4, s_lo0 = (s_base & 0x3FFFFu) >> 4;
+        int sv = 0, ss = 0;
+        uint32_t pv = 0, ps = 0, pt = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const WgUnit u = wg_decode<BLOCK_N, STACKED>(p, unit);
+            const int ncols = STACKED ? u.scols : u.vcols;
+            const int nmma = ((ncols + cwB - 1) / cwB) * cwB;  // whole loaded boxes
+            const uint32_t idesc = make_idesc_bf16(WG_BLOCK_M, nmma, 1, 1);
+            const int rb_begin = u.split * p.rb_per_split;
+            const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
+            mbar_wait(tempty, pt ^ 1u, p.err_flag, 700);
+            tc_fence_after();
+            uint32_t accum = 0;
+            for (int rb = rb_begin; rb < rb_end; ++rb) {
+                mbar_wait(sfull(ss), ps, p.err_flag, 600 + ss);
+                const uint32_t s_lo = s_lo0 + ss * (Cfg::S_BYTES >> 4);
+                uint32_t d_tmem = tmem_base;
+                for (int g = 0; g < u.ngr; ++g, d_tmem += BLOCK_N) {
+                    mbar_wait(vfull(sv), pv, p.err_flag, 620 + sv);
+                    tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t v_lo = v_lo0 + sv * (Cfg::V_BYTES >> 4);
                         const uint64_t adesc = hiA | (STACKED ? v_lo : s_lo);
                         const uint64_t bdesc = hiB | (STACKED ? s_lo : v_lo);
@@ -286,21 +290,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                         umma_bf16(d_tmem, adesc + 2 * stepA, bdesc + 2 * stepB, idesc, 1u);
                         umma_bf16(d_tmem, adesc + 3 * stepA, bdesc + 3 * stepB, idesc, 1u);
                         umma_commit(vempty(sv));
-                        if (++sv == SV) {
-                            sv = 0;
-                            pv ^= 1u;
-                        }
                     }
-                    accum = 1u;
-                    umma_commit(sempty(ss));  // after the MMAs of every group that read this dz box
-                    if (++ss == SS) {
-                        ss = 0;
-                        ps ^= 1u;
+                    __syncwarp();
+                    if (++sv == SV) {
+                        sv = 0;
+                        pv ^= 1u;
                     }
                 }
-                umma_commit(tfull);
-                pt ^= 1u;
+                accum = 1u;
+                if (elect_one()) umma_commit(sempty(ss));  // after the MMAs of every group that read this dz box
+                __syncwarp();
+                if (++ss == SS) {
+                    ss = 0;
+                    ps ^= 1u;
+                }
             }
+            if (elect_one()) umma_commit(tfull);
+            __syncwarp();
+            pt ^= 1u;
         }
     } else if (warp >= 4) {
         // =================================== epilogue =======================================
