@@ -170,12 +170,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
-        // The warp runs converged and ONE elected lane (elect.sync) issues every copy -- straight-line
-        // UTMALDG code; a divergent per-lane issue makes ptxas wrap each copy in an ELECT/branch loop.
-        // Lane l still PRECOMPUTES the tap shift and channel offset of "its" (tap group, box) pair of
-        // the varying operand once per unit; the elected lane fetches them with a shuffle, so the
-        // per-block work is a few adds per copy; the pixel-block coordinates are carried by nested
-        // counters (no divisions in the loop).
+        // The warp runs converged and ONE elected lane (elect.sync) issues every copy of a stage in one
+        // straight-line block of UTMALDGs; under a divergent per-lane guard ptxas wraps each copy in an
+        // ELECT/branch loop.  All coordinates are warp-uniform: the first tap of every group is
+        // decoded once per unit (registers, the group loop is unrolled), the pixel-block coordinates
+        // are carried by nested counters (no divisions in the loop).
+        constexpr int MAX_GU = Cfg::MAX_GU;
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -184,17 +184,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             const int boxesV = STACKED ? p.G : (u.vcols + cwV - 1) / cwV;
             const int rb_begin = u.split * p.rb_per_split;
             const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-            // this lane's varying box: group my_g, box my_i -> packed (dx, dy, channel offset)
-            const int my_g = lane / boxesV, my_i = lane - my_g * boxesV;
-            int my_pack = 0;
-            if (my_g < u.ngr) {
-                const int grp = u.gset * p.GU + my_g;
-                // stacked: taps beyond the filter repeat the last one; their rows are never stored
-                const int tp = STACKED ? min(grp * p.G + my_i, p.taps - 1) : grp;
-                const int sy = tp / p.ksize;
-                const int dy = sy - p.pad, dx = tp - sy * p.ksize - p.pad;
-                const int c = STACKED ? 0 : u.v0 + my_i * cwV;
-                my_pack = (c << 8) | ((dy + 8) << 4) | (dx + 8);
+            // first tap (kx, ky) of every group of this unit
+            int gkx[MAX_GU], gky[MAX_GU];
+#pragma unroll
+            for (int g = 0; g < MAX_GU; ++g) {
+                const int tp = (u.gset * p.GU + g) * p.G;
+                gky[g] = tp / p.ksize;
+                gkx[g] = tp - gky[g] * p.ksize;
             }
             const uint32_t s_tx = boxesS * boxS_bytes, v_tx = boxesV * boxV_bytes;
             // pixel-block counters
@@ -222,21 +218,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                     ps ^= 1u;
                 }
                 // varying operand: one stage per tap group
-                int src_lane = 0;
-                for (int g = 0; g < u.ngr; ++g) {
-                    mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
-                    uint32_t dst = v_base + sv * Cfg::V_BYTES;
-                    if (elect_one()) mbar_arrive_expect_tx(vfull(sv), v_tx);
-                    for (int i = 0; i < boxesV; ++i, ++src_lane, dst += boxV_bytes) {
-                        const int pk = __shfl_sync(0xffffffffu, my_pack, src_lane);
-                        if (elect_one())
-                            tma_load_5d(dst, &tm_src, vfull(sv), pk >> 8, w0 + (pk & 15) - 8, h0 + ((pk >> 4) & 15) - 8,
-                                        b0, t);
-                    }
-                    __syncwarp();
-                    if (++sv == SV) {
-                        sv = 0;
-                        pv ^= 1u;
+#pragma unroll
+                for (int g = 0; g < MAX_GU; ++g) {
+                    if (g < u.ngr) {
+                        mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
+                        if (elect_one()) {
+                            const uint32_t fb = vfull(sv);
+                            mbar_arrive_expect_tx(fb, v_tx);
+                            uint32_t dst = v_base + sv * Cfg::V_BYTES;
+                            if (STACKED) {
+                                // G consecutive taps; taps beyond the filter repeat the last one (their
+                                // rows are never stored)
+                                int kx = gkx[g], ky = gky[g];
+                                for (int i = 0; i < boxesV; ++i, dst += boxV_bytes) {
+                                    tma_load_5d(dst, &tm_src, fb, 0, w0 + kx - p.pad, h0 + ky - p.pad, b0, t);
+                                    if (ky * p.ksize + kx + 1 < p.taps) {
+                                        if (++kx == p.ksize) {
+                                            kx = 0;
+                                            ++ky;
+                                        }
+                                    }
+                                }
+                            } else {
+                                const int cw = w0 + gkx[g] - p.pad, chh = h0 + gky[g] - p.pad;
+                                int c = u.v0;
+                                for (int i = 0; i < boxesV; ++i, dst += boxV_bytes, c += cwV)
+                                    tma_load_5d(dst, &tm_src, fb, c, cw, chh, b0, t);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sv == SV) {
+                            sv = 0;
+                            pv ^= 1u;
+                        }
                     }
                 }
                 if (++wt == p.tiles_w) {
@@ -450,9 +464,6 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     p.ngroups = (p.taps + p.G - 1) / p.G;
     p.GU = 512 / block_n;
     if (p.GU > p.ngroups) p.GU = p.ngroups;
-    // the producer warp gives every (group, box) pair of the varying operand its own lane
-    const int boxes_v = stacked ? p.G : ((Csrc < block_n ? Csrc : block_n) + p.cwV - 1) / p.cwV;
-    while (p.GU > 1 && p.GU * boxes_v > 32) --p.GU;
     // balance the group sets (e.g. 9 taps, at most 4 accumulators -> 3+3+3 rather than 4+4+1)
     p.ngsets = (p.ngroups + p.GU - 1) / p.GU;
     p.GU = (p.ngroups + p.ngsets - 1) / p.ngsets;
