@@ -41,6 +41,15 @@ int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, 
                      long long ld0, int split, void* dst1, long long ld1, int out_fp32, int relu,
                      int accumulate, void* stream);
 
+/* The first half of a DoubleConv stage (unet.py:70-71): the same convolution with the training-mode
+ * nn.BatchNorm2d batch statistics of its output fused into the epilogue.  dst: bf16 [T][B][H][W][N]
+ * (contiguous); stat_sum / stat_sumsq: fp64 [T][N], zeroed here and filled with the per-(t, channel) sum
+ * and sum of squares over (B, H, W) of the stored (bf16) outputs -- the input of b200_bn_finalize, so
+ * b200_bn_stats and its extra pass over dst are not needed. */
+int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H, int W,
+                             const void* wpacked, const float* bias, int N, int ksize, void* dst,
+                             double* stat_sum, double* stat_sumsq, void* stream);
+
 /* One ConvLSTM cell step, ConvLSTMCell.forward (unet.py:21-36): gate conv over [x ; h_prev] fused
  * with sigmoid/tanh and the c/h update.  wpacked: bf16 [k*k][4*Ch gate-interleaved][Cin+Ch];
  * bias_packed fp32 [4*Ch] in the same row order (b200_pack_lstm_weights).  h_prev / c_prev may be

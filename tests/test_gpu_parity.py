@@ -349,6 +349,38 @@ def test_conv_tc_vs_simt(T, B, H, W, C0, C1, N, ks):
         assert rel(_np(got), _np(refd)) < 6e-3
 
 
+@pytest.mark.parametrize("T,B,H,W,C0,C1,N", [(3, 4, 64, 64, 64, 0, 64),     # halo kernel, resident weights
+                                             (2, 5, 32, 32, 128, 128, 128),  # halo, two sources, streamed weights
+                                             (3, 6, 8, 8, 256, 0, 512),      # generic kernel, two N tiles
+                                             (2, 3, 16, 16, 64, 0, 48),      # N not a multiple of the N tile
+                                             (2, 7, 4, 4, 128, 0, 256),      # batch tail rows outside the tensor
+                                             (2, 2, 64, 64, 16, 0, 64)])     # first layer (16-channel K chunk)
+def test_conv_fused_bn_stats(T, B, H, W, C0, C1, N):
+    """The BatchNorm sums produced by the conv epilogue (b200_conv_bnstats_tc_fwd) equal the sums of the
+    stored bf16 output (b200_bn_stats), and the output itself is unchanged."""
+    from unet_convlstm_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x0 = torch.randn(T, B, H, W, C0, device="cuda", generator=g).bfloat16()
+    x1 = torch.randn(T, B, H, W, C1, device="cuda", generator=g).bfloat16() if C1 else None
+    w = torch.randn(N, C0 + C1, 3, 3, device="cuda", generator=g) / ((C0 + C1) * 9) ** 0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    wp = ops.pack_conv_weight(w, torch.bfloat16)
+    plain = torch.empty((T, B, H, W, N), device="cuda", dtype=torch.bfloat16)
+    assert ops.conv_fwd(x0, x1, wp, bias, 3, plain) is False
+    out = torch.full((T, B, H, W, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ws = torch.full((2, T, N), float("nan"), device="cuda", dtype=torch.float64)
+    assert ops.conv_fwd(x0, x1, wp, bias, 3, out, bn_ws=ws) is True
+    assert torch.equal(out, plain)
+    ref = torch.empty((2, T, N), device="cuda", dtype=torch.float64)
+    _lib.call("b200_bn_stats", out.data_ptr(), T, B * H * W, N, 0, ref[0].data_ptr(), ref[1].data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    exact = out.double().reshape(T, -1, N)
+    np.testing.assert_allclose(_np(ws[0]), _np(exact.sum(1)), rtol=0, atol=2e-5 * B * H * W)
+    np.testing.assert_allclose(_np(ws[1]), _np((exact * exact).sum(1)), rtol=2e-5)
+    np.testing.assert_allclose(_np(ws[0]), _np(ref[0]), rtol=0, atol=2e-5 * B * H * W)
+    np.testing.assert_allclose(_np(ws[1]), _np(ref[1]), rtol=2e-5)
+
+
 @pytest.mark.parametrize("T,B,H,W,Nz,C0,C1,ks", [(1, 2, 8, 8, 128, 64, 0, 3), (2, 4, 4, 4, 256, 128, 128, 3),
                                                  (3, 2, 16, 16, 64, 64, 0, 3), (2, 2, 32, 32, 128, 32, 96, 3),
                                                  (1, 1, 12, 16, 64, 16, 0, 3), (2, 2, 8, 128, 320, 320, 0, 1),

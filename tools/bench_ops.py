@@ -47,12 +47,27 @@ def bench_conv(K, N, HW, T=20, B=256, ks=3):
     print(f"conv K{K} N{N} {HW}x{HW} T{T} B{B}: {ms:8.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
+def bench_convbn(K, N, HW, T=20, B=256, ks=3):
+    x = torch.randn(T, B, HW, HW, K, device=dev).to(bf)
+    wp = (torch.randn(ks * ks, N, K, device=dev) * 0.05).to(bf)
+    bias = torch.randn(N, device=dev)
+    out = torch.empty(T, B, HW, HW, N, device=dev, dtype=bf)
+    ws = torch.empty(2, T, N, device=dev, dtype=torch.float64)
+    fl = 2.0 * T * B * HW * HW * ks * ks * K * N
+    ms = timeit(lambda: ops.conv_fwd(x, None, wp, bias, ks, out))
+    print(f"conv        K{K} N{N} {HW}x{HW} T{T} B{B}: {ms:8.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
+    ms = timeit(lambda: ops.conv_fwd(x, None, wp, bias, ks, out, bn_ws=ws))
+    print(f"conv+bnstat K{K} N{N} {HW}x{HW} T{T} B{B}: {ms:8.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     a = sys.argv[1:]
     if a[0] == "wgrad":
         bench_wgrad(*[int(v) for v in a[1:]])
     elif a[0] == "conv":
         bench_conv(*[int(v) for v in a[1:]])
+    elif a[0] == "convbn":
+        bench_convbn(*[int(v) for v in a[1:]])
     else:
         for Nz, C, HW in [(64, 64, 64), (64, 16, 64), (128, 64, 32), (128, 128, 32), (256, 128, 16), (256, 256, 16),
                           (512, 512, 8), (1024, 1024, 4)]:

@@ -31,10 +31,11 @@ extern "C" int b200_conv_tc_supported(int B, int H, int W, int C0, int C1, int N
     return 1;
 }
 
-extern "C" int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
-                                int W, const void* wpacked, const float* bias, int N, int ksize,
-                                void* dst0, long long ld0, int split, void* dst1, long long ld1,
-                                int out_fp32, int relu, int accumulate, void* stream) {
+static int conv_tc_fwd_impl(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
+                           int W, const void* wpacked, const float* bias, int N, int ksize,
+                           void* dst0, long long ld0, int split, void* dst1, long long ld1,
+                           int out_fp32, int relu, int accumulate, double* stat_sum, double* stat_sumsq,
+                           void* stream) {
     if (!src0 || !wpacked || !dst0 || T <= 0 || N <= 0 || (ksize & 1) == 0) {
         set_last_error("b200_conv_tc_fwd: bad arguments");
         return B200_ERR_ARG;
@@ -59,13 +60,36 @@ extern "C" int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int 
     if (halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
         conv_halo_supported(T * B, H, W, C0, C1, N, ksize))
         return launch_conv_halo(src0, src1, wpacked, T * B, H, W, C0, C1, N, bias, dst0, ld0, split, dst1, ld1,
-                                out_fp32, relu, accumulate, static_cast<cudaStream_t>(stream));
+                                out_fp32, relu, accumulate, stat_sum, stat_sumsq, B, static_cast<cudaStream_t>(stream));
     ConvTcParams p = {};
     p.T = T; p.B = B; p.H = H; p.W = W;
     p.C0 = C0; p.C1 = C1; p.N = N; p.ksize = ksize;
     p.dst0 = dst0; p.dst1 = dst1; p.ld0 = ld0; p.ld1 = ld1; p.split = split;
     p.out_fp32 = out_fp32; p.relu = relu; p.accumulate = accumulate; p.bias = bias;
+    p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
     return launch_conv_tc(src0, src1, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
+                                int W, const void* wpacked, const float* bias, int N, int ksize,
+                                void* dst0, long long ld0, int split, void* dst1, long long ld1,
+                                int out_fp32, int relu, int accumulate, void* stream) {
+    return conv_tc_fwd_impl(src0, C0, src1, C1, T, B, H, W, wpacked, bias, N, ksize, dst0, ld0, split, dst1, ld1,
+                            out_fp32, relu, accumulate, nullptr, nullptr, stream);
+}
+
+extern "C" int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
+                                        int W, const void* wpacked, const float* bias, int N, int ksize, void* dst,
+                                        double* stat_sum, double* stat_sumsq, void* stream) {
+    if (!stat_sum || !stat_sumsq) {
+        set_last_error("b200_conv_bnstats_tc_fwd: statistics buffers are required");
+        return B200_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B200_CUDA_CHECK(cudaMemsetAsync(stat_sum, 0, sizeof(double) * T * N, st));
+    B200_CUDA_CHECK(cudaMemsetAsync(stat_sumsq, 0, sizeof(double) * T * N, st));
+    return conv_tc_fwd_impl(src0, C0, src1, C1, T, B, H, W, wpacked, bias, N, ksize, dst, N, N, nullptr, 0,
+                            /*out_fp32=*/0, /*relu=*/0, /*accumulate=*/0, stat_sum, stat_sumsq, stream);
 }
 
 extern "C" int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch, int B, int H,

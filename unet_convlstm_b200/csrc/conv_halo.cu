@@ -45,6 +45,10 @@ struct ConvHaloParams {
     long long ld0, ld1;
     int split, out_fp32, relu, accumulate;
     const float* bias;
+    // fused BatchNorm statistics (see ConvTcParams::stat_sum): [IMG / imgs_per_t][N]
+    double* stat_sum;
+    double* stat_sumsq;
+    int imgs_per_t;
     int* err_flag;
 };
 
@@ -73,6 +77,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     const uint32_t tmem_ptr_addr = wfull + 8u * 5;
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    // [8 epilogue warps][2][BLOCK_N / 2] floats after the 256-byte barrier area
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -267,9 +273,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         constexpr int COLS = BLOCK_N / 2;  // columns handled by this warp
         int acc = 0;
         uint32_t acc_phase = 0;
+        // fused BatchNorm statistics: per-warp partial sums in shared memory (plain read-modify-write by
+        // the owning lane), flushed with fp64 atomics when the (t, N tile) key changes (see conv_tc.cu)
+        const bool do_stats = p.stat_sum != nullptr;
+        float* stat_row = stat_smem + e * (2 * COLS);
+        int stat_t = -1, stat_n0 = 0;
+        auto stat_flush = [&]() {
+            __syncwarp();
+            for (int i = lane; i < 2 * COLS; i += 32) {
+                const float v = stat_row[i];
+                stat_row[i] = 0.f;
+                const int col = stat_n0 + half * COLS + (i % COLS);
+                if (col < p.N && stat_t >= 0)
+                    atomicAdd((i < COLS ? p.stat_sum : p.stat_sumsq) + static_cast<long long>(stat_t) * p.N + col,
+                              static_cast<double>(v));
+            }
+            __syncwarp();
+        };
+        if (do_stats) stat_flush();  // zeroes the buffer
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int n0, img, q0, r0;
             decode(tile, n0, img, q0, r0);
+            if (do_stats) {
+                const int tt = img / p.imgs_per_t;
+                if (tt != stat_t || n0 != stat_n0) {
+                    if (stat_t >= 0) stat_flush();
+                    stat_t = tt;
+                    stat_n0 = n0;
+                }
+            }
             const int q = q0 + r;
             const int h = q / p.P;
             const int w = q - h * p.P;
@@ -285,6 +317,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 uint32_t v[32];
                 tmem_ld32(t_row + c32 * 32, v);
                 tmem_ld_wait();
+                if (do_stats) {
+#pragma unroll
+                    for (int g16 = 0; g16 < 2; ++g16) {
+                        if (ncol + g16 * 16 >= p.N) break;
+                        float s1[16], s2[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float x = __uint_as_float(v[g16 * 16 + j]);
+                            if (p.bias) x += __ldg(p.bias + ncol + g16 * 16 + j);
+                            x = valid ? __bfloat162float(__float2bfloat16_rn(x)) : 0.f;
+                            s1[j] = x;
+                            s2[j] = x * x;
+                        }
+                        warp_colsum16(s1, lane);
+                        warp_colsum16(s2, lane);
+                        if ((lane & 1) == 0) {
+                            const int col = c32 * 32 + g16 * 16 + stat_col(lane);
+                            stat_row[col] += s1[0];
+                            stat_row[COLS + col] += s2[0];
+                        }
+                    }
+                }
                 if (!valid) continue;
                 const int nv = min(32, p.N - ncol);  // multiple of 16
 #pragma unroll
@@ -337,6 +391,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 acc_phase ^= 1u;
             }
         }
+        if (do_stats && stat_t >= 0) stat_flush();
     }
 
     tc_fence_before();
@@ -366,7 +421,7 @@ static bool plan_halo(int IMG, int H, int W, int C0, int C1, int N, int ksize, i
     p->a_box_bytes = static_cast<uint32_t>(p->RB) * p->P * 128u;
     p->a_stage_bytes = (p->a_box_bytes + 1023u) & ~1023u;
     p->b_box_bytes = static_cast<uint32_t>(block_n) * 128u;
-    const int fixed = 1024 + 512;  // alignment slack + barriers
+    const int fixed = 1024 + 256 + 8 * block_n * 4;  // alignment slack + barriers + BatchNorm partial sums
     // resident weights if they leave room for >= 2 activation stages (single N tile only)
     const long long wbytes = 9LL * p->chunks * p->b_box_bytes;
     p->wres = 0;
@@ -414,7 +469,8 @@ static int launch_halo_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, cons
 // src0/src1: bf16 [IMG][H][W][C*]; wpacked: bf16 [9][N][C0+C1]; output semantics of EPI_STORE.
 int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, int IMG, int H, int W, int C0, int C1,
                      int N, const float* bias, void* dst0, long long ld0, int split, void* dst1, long long ld1,
-                     int out_fp32, int relu, int accumulate, cudaStream_t stream) {
+                     int out_fp32, int relu, int accumulate, double* stat_sum, double* stat_sumsq, int imgs_per_t,
+                     cudaStream_t stream) {
     ConvHaloParams p = {};
     int smem = 0;
     const int block_n = halo_block_n(N);
@@ -424,6 +480,7 @@ int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, in
     }
     p.dst0 = dst0; p.dst1 = dst1; p.ld0 = ld0; p.ld1 = ld1; p.split = split;
     p.out_fp32 = out_fp32; p.relu = relu; p.accumulate = accumulate; p.bias = bias;
+    p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq; p.imgs_per_t = imgs_per_t > 0 ? imgs_per_t : 1;
     p.err_flag = device_error_flag();
     CUtensorMap ta0, ta1, tb;
     {

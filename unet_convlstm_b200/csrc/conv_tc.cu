@@ -39,7 +39,8 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 4;  // BatchNorm partial sums, one row per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAT_BYTES;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -102,6 +103,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    // [4 epilogue warps][2][BLOCK_N] floats after the 256-byte barrier area
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -266,11 +269,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         const int bi = r / (p.Wt * p.Ht);
         int acc = 0;
         uint32_t acc_phase = 0;
+        // fused BatchNorm statistics: every epilogue warp keeps the partial sums of its 32 rows in its
+        // own shared-memory row (plain read-modify-write by the owning lane: no atomics, no barriers) and
+        // flushes them (fp64 atomics) whenever the (t, N tile) key changes -- tiles are ordered N tile,
+        // t, image, row, so a warp flushes ~T times per N tile
+        const bool do_stats = (EPI == EPI_STORE) && p.stat_sum != nullptr;
+        float* stat_row = stat_smem + q * (2 * BLOCK_N);
+        int stat_t = -1, stat_n0 = 0;
+        auto stat_flush = [&]() {
+            __syncwarp();
+            for (int i = lane; i < 2 * BLOCK_N; i += 32) {
+                const float v = stat_row[i];
+                stat_row[i] = 0.f;
+                const int col = stat_n0 + (i % BLOCK_N);
+                if (col < p.N && stat_t >= 0)
+                    atomicAdd((i < BLOCK_N ? p.stat_sum : p.stat_sumsq) + static_cast<long long>(stat_t) * p.N + col,
+                              static_cast<double>(v));
+            }
+            __syncwarp();
+        };
+        if (do_stats) stat_flush();  // zeroes the buffer (stat_t < 0: nothing is added)
         for (int step = 0; step < nsteps; ++step) {
         const bool zero_state = seq && step == 0 && !p.seq_have_h0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             TileCoord tc = decode_tile(p, tile, BLOCK_N);
             if (seq) tc.t = step;
+            if (do_stats && (tc.t != stat_t || tc.n0 != stat_n0)) {
+                if (stat_t >= 0) stat_flush();
+                stat_t = tc.t;
+                stat_n0 = tc.n0;
+            }
             const bool valid = (tc.h0 + hi < p.H) && (tc.b0 + bi < p.B);
             const long long pix =
                 ((static_cast<long long>(tc.t) * p.B + tc.b0 + bi) * p.H + tc.h0 + hi) * p.W + tc.w0 + wi;
@@ -286,6 +314,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     uint32_t v[16];
                     tmem_ld16(t_row + c16 * 16, v);
                     tmem_ld_wait();
+                    if (do_stats) {
+                        // statistics of the values as stored (bias added, rounded to bf16); rows outside
+                        // the tensor contribute nothing
+                        float s1[16], s2[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float x = __uint_as_float(v[j]);
+                            if (p.bias) x += __ldg(p.bias + ncol + j);
+                            x = valid ? __bfloat162float(__float2bfloat16_rn(x)) : 0.f;
+                            s1[j] = x;
+                            s2[j] = x * x;
+                        }
+                        warp_colsum16(s1, lane);
+                        warp_colsum16(s2, lane);
+                        if ((lane & 1) == 0) {
+                            const int col = c16 * 16 + stat_col(lane);
+                            stat_row[col] += s1[0];
+                            stat_row[BLOCK_N + col] += s2[0];
+                        }
+                    }
                     if (valid) {
                         float f[16];
 #pragma unroll
@@ -410,6 +458,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 acc = 0;
                 acc_phase ^= 1u;
             }
+        }
+        if (do_stats && stat_t >= 0) {
+            stat_flush();
+            stat_t = -1;
         }
         if (seq && step + 1 < nsteps) {
             // publish h_t / c_t of this CTA's tiles, then signal the grid-wide step counter

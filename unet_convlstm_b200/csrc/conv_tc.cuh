@@ -30,6 +30,10 @@ struct ConvTcParams {
     int relu;
     int accumulate;      // fp32 only: dst += value
     const float* bias;   // [N] (packed order) or nullptr
+    // fused BatchNorm statistics (bf16 output only): per (t, column) sum and sum of squares of the
+    // stored (bf16-rounded) outputs are added to stat_sum / stat_sumsq [T][N] (caller zeroes them)
+    double* stat_sum;
+    double* stat_sumsq;
     // EPI_LSTM  (Ch = N/4; packed column = (n_tile*4 + gate)*CHT + j)
     const float* c_prev;        // [P, Ch] fp32 or nullptr (zeros)
     float* c_next;              // [P, Ch] fp32
@@ -56,7 +60,8 @@ int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpa
 bool conv_halo_supported(int IMG, int H, int W, int C0, int C1, int N, int ksize);
 int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, int IMG, int H, int W, int C0, int C1,
                      int N, const float* bias, void* dst0, long long ld0, int split, void* dst1, long long ld1,
-                     int out_fp32, int relu, int accumulate, cudaStream_t stream);
+                     int out_fp32, int relu, int accumulate, double* stat_sum, double* stat_sumsq, int imgs_per_t,
+                     cudaStream_t stream);
 
 // Picks BLOCK_N for a given GEMM N (multiple of 16).  LSTM epilogue needs N % 64 == 0.
 int pick_block_n(int N, int epi);

@@ -196,6 +196,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Epilogue helper: per-column sums over the 32 rows (lanes) of a warp for 16 columns held one row per
+// lane -- a transpose-reduce butterfly, 16 shuffles instead of 16 x 5.  On return v[0] of lane L is the
+// total of column stat_col(L) (lanes L and L^1 hold the same value).
+// ----------------------------------------------------------------------------------------------
+template <int HALF, int BIT>
+__device__ __forceinline__ void warp_colsum_step(float (&v)[16], int lane) {
+    const bool up = (lane & BIT) != 0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        const float send = up ? v[j] : v[j + HALF];
+        const float keep = up ? v[j + HALF] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+    }
+}
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+    warp_colsum_step<8, 16>(v, lane);
+    warp_colsum_step<4, 8>(v, lane);
+    warp_colsum_step<2, 4>(v, lane);
+    warp_colsum_step<1, 2>(v, lane);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int stat_col(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 __device__ __forceinline__ float fast_tanh(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -86,8 +86,14 @@ class ConvBnRelu(torch.autograd.Function):
             raise ValueError(f"conv weight expects {K} input channels, got {C0}+{C1}")
         wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
         z = torch.empty((T, B, H, W, N), device=x0.device, dtype=dt)
-        ops.conv_fwd(x0, x1, wp, bias.detach() if bias is not None else None, ks, z)
-        y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum)
+        # The BatchNorm sums CAN come out of the conv epilogue (b200_conv_bnstats_tc_fwd), but measured on
+        # B200 the cross-lane column reduction makes the epilogue of the narrow layers longer than their
+        # main loop (K64->N64 @64x64: +1.05 ms per call against 0.65 ms for the separate HBM-bound
+        # b200_bn_stats pass, profiles/r01_fused_bn_stats_measured.txt), so it is opt-in.
+        ws = torch.empty((2, T, N), device=x0.device, dtype=torch.float64) if (training and ops.FUSE_BN_STATS) else None
+        fused = ops.conv_fwd(x0, x1, wp, bias.detach() if bias is not None else None, ks, z, bn_ws=ws)
+        y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum,
+                                   ws=ws if fused else None)
         ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
         ctx.tstride = stats[4]
         ctx.training, ctx.cache, ctx.has_bias = training, cache, bias is not None

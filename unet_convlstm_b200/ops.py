@@ -180,9 +180,11 @@ def tc_conv_ok(x0, x1, N, lstm=False) -> bool:
     return _lib.supported("b200_conv_tc_supported", B, H, W, C0, C1, N, int(lstm))
 
 
-def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False):
+def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False, bn_ws=None):
     """out = conv_k([x0 ; x1]) (+bias) (+relu).  x*: [T,B,H,W,C*]; wp: [k*k, N, C0+C1]; the N output
-    columns go to out0 (its last dim) and, if given, the rest to out1 (dgrad of a virtual concat)."""
+    columns go to out0 (its last dim) and, if given, the rest to out1 (dgrad of a virtual concat).
+    bn_ws: optional fp64 [2, T, N] workspace; on the tensor-core path the per-(t, channel) sum and sum of
+    squares of the output are accumulated into it by the conv epilogue.  Returns True if they were."""
     _chk(x0, "x0"), _chk(wp, "wp"), _chk(out0, "out0")
     T, B, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else _chk(x1, "x1").shape[-1]
@@ -197,14 +199,19 @@ def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False):
     ld1 = 0 if out1 is None else out1.shape[-1]
     tag = f"K{C0 + C1} N{N} {H}x{W} k{ksize}"
     work = (2.0 * T * B * H * W * ksize * ksize * (C0 + C1) * N, None)
-    if tc_conv_ok(x0, x1, N) and split % 16 == 0 and out0.shape[-1] % 8 == 0 and ld1 % 8 == 0:
+    tc = tc_conv_ok(x0, x1, N) and split % 16 == 0 and out0.shape[-1] % 8 == 0 and ld1 % 8 == 0
+    if tc and bn_ws is not None and out1 is None and not relu and out0.dtype == torch.bfloat16:
+        _lib.call("b200_conv_bnstats_tc_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(bias), N, ksize,
+                  _p(out0), _p(bn_ws[0]), _p(bn_ws[1]), _st(), tag=tag + " +bnstats", work=work)
+        return True
+    if tc:
         _lib.call("b200_conv_tc_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(bias), N, ksize, _p(out0),
                   out0.shape[-1], split, _p(out1), ld1, _f32(out0), int(relu), 0, _st(), tag=tag, work=work)
     else:
         _lib.call("b200_conv_simt_fwd", _p(x0), C0, _p(x1), C1, T * B, H, W, _p(wp), _p(bias), N, ksize,
                   _p(out0), out0.shape[-1], split, _p(out1), ld1, _f32(x0), _f32(out0), int(relu), _st(),
                   tag=tag, work=work)
-    return out0
+    return False
 
 
 def conv_wgrad(dz, src, ksize, dw, koff):
@@ -237,8 +244,9 @@ def colsum(x2d_rows: int, x, C: int, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------------
 # BatchNorm + ReLU
 # ------------------------------------------------------------------------------------------------
-def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum):
-    """Returns (y, stats) with stats = (mean, rstd, scale, shift, tstride); statistics per (t, c)."""
+def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum, ws=None):
+    """Returns (y, stats) with stats = (mean, rstd, scale, shift, tstride); statistics per (t, c).
+    ws: fp64 [2, T, C] sums already produced by the conv epilogue (conv_fwd(..., bn_ws=ws))."""
     _chk(z, "z")
     T, B, H, W, C = z.shape
     P = B * H * W
@@ -249,9 +257,10 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
     scale = torch.empty_like(mean)
     shift = torch.empty_like(mean)
     if training:
-        ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
-        _lib.call("b200_bn_stats", _p(z), T, P, C, _f32(z), _p(ws[0]), _p(ws[1]), _st(),
-                  tag=f"C{C} {H}x{W}", work=(None, z.numel() * z.element_size()))
+        if ws is None:
+            ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
+            _lib.call("b200_bn_stats", _p(z), T, P, C, _f32(z), _p(ws[0]), _p(ws[1]), _st(),
+                      tag=f"C{C} {H}x{W}", work=(None, z.numel() * z.element_size()))
         _lib.call("b200_bn_finalize", _p(ws[0]), _p(ws[1]), T, P, C, _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), eps, momentum, 1, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     else:
@@ -359,6 +368,9 @@ def lstm_tc_ok(x_t, Ch) -> bool:
     B, H, W, Cin = x_t.shape
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
+
+# BatchNorm batch statistics in the conv epilogue instead of a separate pass (slower on B200, see functional.py)
+FUSE_BN_STATS = os.environ.get("B200_FUSE_BN_STATS", "0") == "1"
 
 # One cooperative timestep-persistent launch per ConvLSTM layer (default) or one launch per timestep
 PERSISTENT_LSTM = os.environ.get("B200_PERSISTENT_LSTM", "1") != "0"
