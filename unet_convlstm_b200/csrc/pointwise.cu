@@ -49,6 +49,43 @@ __device__ __forceinline__ void ldv(const T* __restrict__ p, float (&f)[V]) {
     }
 }
 
+// Raw (not yet converted) vector of V elements: lets a loop issue several independent 16-byte loads
+// before the first conversion, so enough bytes are in flight to cover the HBM latency.
+template <typename T, int V>
+struct RawVec {
+    static constexpr int NW = (V == 1) ? 1 : 4;
+    uint32_t w[NW];
+};
+template <typename T, int V>
+__device__ __forceinline__ void ld_raw(const T* __restrict__ p, RawVec<T, V>& r) {
+    if constexpr (V == 1) {
+        if constexpr (std::is_same<T, float>::value)
+            r.w[0] = __float_as_uint(p[0]);
+        else
+            r.w[0] = static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(p)) << 16;
+    } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        r.w[0] = t.x; r.w[1] = t.y; r.w[2] = t.z; r.w[3] = t.w;
+    }
+}
+template <typename T, int V>
+__device__ __forceinline__ void unpack_raw(const RawVec<T, V>& r, float (&f)[V]) {
+    if constexpr (V == 1) {
+        f[0] = __uint_as_float(r.w[0]);
+    } else if constexpr (std::is_same<T, float>::value) {
+        static_assert(V == 4, "fp32 vectors are 4 wide");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = __uint_as_float(r.w[j]);
+    } else {
+        static_assert(V == 8, "bf16 vectors are 8 wide");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[2 * j] = __uint_as_float(r.w[j] << 16);
+            f[2 * j + 1] = __uint_as_float(r.w[j] & 0xffff0000u);
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -102,9 +139,11 @@ struct ReduceGeom {
     long long rows_per_block;
 };
 
-// Op::accum(t, row, c, a0, a1): adds the contribution of V channels starting at c of one row.
+// Op::load(frag, t, row, c) fetches the raw operands of V channels starting at c of one row;
+// Op::accum(state, frag, a0, a1) adds their contribution.  The row loop loads COLRED_U rows ahead.
+static constexpr int COLRED_U = 4;
 template <typename T, int V, typename Acc, typename Op>
-__global__ void __launch_bounds__(256) colreduce_kernel(const Op op, const ReduceGeom g, double* __restrict__ out0,
+__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : 4)) colreduce_kernel(const Op op, const ReduceGeom g, double* __restrict__ out0,
                                                         double* __restrict__ out1) {
     __shared__ Acc red[2][256 * (V > 4 ? 4 : V)];  // reduced in two halves when V == 8
     const int tid = threadIdx.x;
@@ -123,9 +162,21 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const Op op, const Reduc
     if (active) {
         typename Op::template State<V> st;  // per-thread coefficients, loaded once
         op.template init<V>(t, c, st);
-#pragma unroll 4
-        for (long long p = p_begin + r; p < p_end; p += g.rows_per_iter)
-            op.template accum<T, V, Acc>(st, t, p, c, a0, a1);
+        const long long step = g.rows_per_iter;
+        long long p = p_begin + r;
+        // main loop: COLRED_U independent rows per trip, every load issued before the first use
+        for (; p + (COLRED_U - 1) * step < p_end; p += COLRED_U * step) {
+            typename Op::template Frag<T, V> fr[COLRED_U];
+#pragma unroll
+            for (int u = 0; u < COLRED_U; ++u) op.template load<T, V>(fr[u], t, p + u * step, c);
+#pragma unroll
+            for (int u = 0; u < COLRED_U; ++u) op.template accum<T, V, Acc>(st, fr[u], a0, a1);
+        }
+        for (; p < p_end; p += step) {
+            typename Op::template Frag<T, V> fr;
+            op.template load<T, V>(fr, t, p, c);
+            op.template accum<T, V, Acc>(st, fr, a0, a1);
+        }
     }
     // combine the rows_per_iter partial sums of each channel
     constexpr int HV = V > 4 ? 4 : V;
@@ -147,6 +198,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const Op op, const Reduc
                     s1 += static_cast<double>(red[1][(rr * g.cvb + cv) * HV + j]);
                 }
                 const long long o = static_cast<long long>(t) * g.C + c + half * HV + j;
+                op.post(t, c + half * HV + j, s0, s1);
                 atomicAdd(out0 + o, s0);
                 if (out1) atomicAdd(out1 + o, s1);
             }
@@ -190,17 +242,25 @@ struct NoState {
     struct State {};
     template <int V>
     __device__ __forceinline__ void init(int, int, State<V>&) const {}
+    __device__ __forceinline__ void post(int, int, double&, double&) const {}
 };
 
 struct StatsOp : NoState {
     const void* x;
     long long P;
     int C;
+    template <typename T, int V>
+    struct Frag {
+        RawVec<T, V> x;
+    };
+    template <typename T, int V>
+    __device__ __forceinline__ void load(Frag<T, V>& fr, int t, long long p, int c) const {
+        ld_raw<T, V>(static_cast<const T*>(x) + (static_cast<long long>(t) * P + p) * C + c, fr.x);
+    }
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(const State<V>&, int t, long long p, int c, Acc (&a0)[V],
-                                          Acc (&a1)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>&, const Frag<T, V>& fr, Acc (&a0)[V], Acc (&a1)[V]) const {
         float f[V];
-        ldv<T, V>(static_cast<const T*>(x) + (static_cast<long long>(t) * P + p) * C + c, f);
+        unpack_raw<T, V>(fr.x, f);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             a0[j] += Acc(f[j]);
@@ -223,10 +283,18 @@ int launch_bn_stats(const void* x, int T_, long long P, int C, int dtype_fp32, d
 struct ColsumOp : NoState {
     const void* x;
     int C;
+    template <typename T, int V>
+    struct Frag {
+        RawVec<T, V> x;
+    };
+    template <typename T, int V>
+    __device__ __forceinline__ void load(Frag<T, V>& fr, int, long long p, int c) const {
+        ld_raw<T, V>(static_cast<const T*>(x) + p * C + c, fr.x);
+    }
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(const State<V>&, int, long long p, int c, Acc (&a0)[V], Acc (&)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>&, const Frag<T, V>& fr, Acc (&a0)[V], Acc (&)[V]) const {
         float f[V];
-        ldv<T, V>(static_cast<const T*>(x) + p * C + c, f);
+        unpack_raw<T, V>(fr.x, f);
 #pragma unroll
         for (int j = 0; j < V; ++j) a0[j] += Acc(f[j]);
     }
@@ -251,9 +319,11 @@ struct BnBwdReduceOp {
     long long P;
     int C;
     int tstride;  // C in training mode, 0 in eval mode (one set of statistics for every t)
+    // Only the ReLU mask needs coefficients inside the loop: the kernel accumulates sum g and sum g*x and
+    // the block epilogue turns the second into sum g*xhat = rstd * (sum g*x - mean * sum g) in fp64.
     template <int V>
     struct State {
-        float sc[V], sh[V], mu[V], rs[V];
+        float sc[V], sh[V];
     };
     template <int V>
     __device__ __forceinline__ void init(int t, int c, State<V>& st) const {
@@ -262,24 +332,34 @@ struct BnBwdReduceOp {
             const int i = t * tstride + c + j;
             st.sc[j] = __ldg(scale + i);
             st.sh[j] = __ldg(shift + i);
-            st.mu[j] = __ldg(mean + i);
-            st.rs[j] = __ldg(rstd + i);
         }
     }
+    __device__ __forceinline__ void post(int t, int c, double& s0, double& s1) const {
+        const int i = t * tstride + c;
+        s1 = static_cast<double>(__ldg(rstd + i)) * (s1 - static_cast<double>(__ldg(mean + i)) * s0);
+    }
+    template <typename T, int V>
+    struct Frag {
+        RawVec<T, V> x, d;
+    };
+    template <typename T, int V>
+    __device__ __forceinline__ void load(Frag<T, V>& fr, int t, long long p, int c) const {
+        const long long off = (static_cast<long long>(t) * P + p) * C + c;
+        ld_raw<T, V>(static_cast<const T*>(x) + off, fr.x);
+        ld_raw<T, V>(static_cast<const T*>(dy) + off, fr.d);
+    }
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(const State<V>& st, int t, long long p, int c, Acc (&a0)[V],
+    __device__ __forceinline__ void accum(const State<V>& st, const Frag<T, V>& fr, Acc (&a0)[V],
                                           Acc (&a1)[V]) const {
         float fx[V], fd[V];
-        const long long off = (static_cast<long long>(t) * P + p) * C + c;
-        ldv<T, V>(static_cast<const T*>(x) + off, fx);
-        ldv<T, V>(static_cast<const T*>(dy) + off, fd);
+        unpack_raw<T, V>(fr.x, fx);
+        unpack_raw<T, V>(fr.d, fd);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const float yv = fmaf(fx[j], st.sc[j], st.sh[j]);
             const float gq = yv > 0.f ? fd[j] : 0.f;
-            const float xh = (fx[j] - st.mu[j]) * st.rs[j];
             a0[j] += Acc(gq);
-            a1[j] += Acc(gq) * Acc(xh);
+            a1[j] += Acc(gq) * Acc(fx[j]);
         }
     }
 };
@@ -300,13 +380,22 @@ struct OutconvWgradOp : NoState {
     const void* x;
     const float* dy;  // [P][O] fp32
     int C, O, o;
+    template <typename T, int V>
+    struct Frag {
+        RawVec<T, V> x;
+        float d;
+    };
+    template <typename T, int V>
+    __device__ __forceinline__ void load(Frag<T, V>& fr, int, long long p, int c) const {
+        ld_raw<T, V>(static_cast<const T*>(x) + p * C + c, fr.x);
+        fr.d = __ldg(dy + p * O + o);
+    }
     template <typename T, int V, typename Acc>
-    __device__ __forceinline__ void accum(const State<V>&, int, long long p, int c, Acc (&a0)[V], Acc (&)[V]) const {
+    __device__ __forceinline__ void accum(const State<V>&, const Frag<T, V>& fr, Acc (&a0)[V], Acc (&)[V]) const {
         float f[V];
-        ldv<T, V>(static_cast<const T*>(x) + p * C + c, f);
-        const float d = __ldg(dy + p * O + o);
+        unpack_raw<T, V>(fr.x, f);
 #pragma unroll
-        for (int j = 0; j < V; ++j) a0[j] += Acc(d) * Acc(f[j]);
+        for (int j = 0; j < V; ++j) a0[j] += Acc(fr.d) * Acc(f[j]);
     }
 };
 
@@ -534,12 +623,10 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
     long long p_end = p_begin + g.rows_per_block;
     if (p_end > g.P) p_end = g.P;
     const long long base = static_cast<long long>(t) * g.P;
-#pragma unroll 4
-    for (long long p = p_begin + r; p < p_end; p += g.rows_per_iter) {
-        const long long off = (base + p) * g.C + c;
+    auto apply = [&](const RawVec<T, V>& rx, const RawVec<T, V>& rd, long long off) {
         float fx[V], fd[V];
-        ldv<T, V>(x + off, fx);
-        ldv<T, V>(dy + off, fd);
+        unpack_raw<T, V>(rx, fx);
+        unpack_raw<T, V>(rd, fd);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const float yv = fmaf(fx[j], sc[j], sh[j]);
@@ -547,6 +634,28 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
             fd[j] = sc[j] * (gq - c1[j] - (fx[j] - mu[j]) * rc2[j]);
         }
         stv<T, V>(dx + off, fd);
+    };
+    // U independent rows per trip: all 2U loads are issued before the first use
+    constexpr int U = 4;
+    const long long step = g.rows_per_iter;
+    long long p = p_begin + r;
+    for (; p + (U - 1) * step < p_end; p += U * step) {
+        RawVec<T, V> rx[U], rd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long off = (base + p + u * step) * g.C + c;
+            ld_raw<T, V>(x + off, rx[u]);
+            ld_raw<T, V>(dy + off, rd[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) apply(rx[u], rd[u], (base + p + u * step) * g.C + c);
+    }
+    for (; p < p_end; p += step) {
+        const long long off = (base + p) * g.C + c;
+        RawVec<T, V> rx, rd;
+        ld_raw<T, V>(x + off, rx);
+        ld_raw<T, V>(dy + off, rd);
+        apply(rx, rd, off);
     }
 }
 
