@@ -527,3 +527,23 @@ def test_lstm_persistent_sequence_kernel_matches_stepwise(T, B, H, W, C, have_h0
     for a, b_ in zip(res[0], res[1]):
         assert not torch.isnan(a.float()).any()
         assert torch.equal(a, b_)
+
+
+def test_wgrad_tc_long_reduction_multi_producer():
+    """Many reduction blocks per unit and tap-group sets of different sizes (2,2,2,2,1): the producer
+    warps of wgrad_tc.cu must stay within one lap of the stage ring (a producer that skipped the stages
+    of a group set it does not own once ran ahead and corrupted the pipeline)."""
+    from unet_convlstm_b200 import _lib, ops
+    T, B, H, W, Nz, C = 2, 64, 16, 16, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dz = torch.randn(T, B, H, W, Nz, device="cuda", generator=g).bfloat16()
+    src = torch.randn(T, B, H, W, C, device="cuda", generator=g).bfloat16()
+    dw = torch.zeros(9, Nz, C, device="cuda")
+    ops.conv_wgrad(dz, src, 3, dw, 0)
+    ref = torch.zeros(9, Nz, C, device="cuda")
+    dzf, sf = dz.float(), src.float()
+    _lib.call("b200_wgrad_simt", dzf.data_ptr(), Nz, sf.data_ptr(), C, T * B, H, W, 3, ref.data_ptr(), C, 0, 1,
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert _lib.lib().b200_device_error() == 0
+    assert rel(_np(dw), _np(ref)) < 1e-4

@@ -12,7 +12,8 @@ import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "b200_convlstm.h")
-LIB_PATH = os.path.join(HERE, "libb200convlstm.so")
+# B200_LIB: developer override to A/B two builds of the library in one GPU session (tools/bench_ops.py)
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(HERE, "libb200convlstm.so")
 
 _CTYPES = {
     "int": ctypes.c_int,

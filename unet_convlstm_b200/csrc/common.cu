@@ -38,9 +38,11 @@ int* device_error_flag() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
     if (!flags[dev]) {
+        // pinned, device-mapped host memory (UVA: same pointer on both sides): the host can still read
+        // the barrier id after a watchdog trap has killed the context
         int* p = nullptr;
-        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, sizeof(int));
+        if (cudaHostAlloc(&p, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        *p = 0;
         flags[dev] = p;
     }
     return flags[dev];

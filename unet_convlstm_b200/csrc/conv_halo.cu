@@ -80,7 +80,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
     // [8 epilogue warps][2][BLOCK_N / 2] floats after the 256-byte barrier area
     float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches use the uniform datapath
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -266,7 +266,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         // 8 warps: a TMEM lane quarter (warp % 4) is shared by two warps that split the columns.  With
         // a single warp per scheduler the TMEM-load / bias-load / store latencies were fully exposed and
         // the N = 64 layers were epilogue-bound (tensor pipe 28 % busy, profiles/r01_ncu_conv_halo_*).
-        const int e = warp - 4;
+        const int e = static_cast<int>(threadIdx.x >> 5) - 4;  // vector-register copy: keeps the epilogue arithmetic off the uniform datapath
         const int qw = e & 3;
         const int half = e >> 2;
         const int r = qw * 32 + lane;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, 
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if (v >= target) break;
         if (clock64() - t0 > 8000000000LL) {
-            if (err_flag) atomicExch(err_flag, 900);
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 900;
             __threadfence_system();
             asm volatile("trap;");
         }
@@ -106,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     // [4 epilogue warps][2][BLOCK_N] floats after the 256-byte barrier area
     float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches use the uniform datapath
     const int lane = threadIdx.x & 31;
 
     const int taps = p.ksize * p.ksize;
@@ -262,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
     } else if (warp >= EPI_WARP0) {
         // =================================== epilogue =======================================
-        const int q = warp - EPI_WARP0;  // TMEM lane quarter == warp % 4
+        const int q = static_cast<int>(threadIdx.x >> 5) - EPI_WARP0;  // TMEM lane quarter == warp % 4 (vector-register copy)
         const int r = q * 32 + lane;     // row of the M tile
         const int wi = r % p.Wt;
         const int hi = (r / p.Wt) % p.Ht;

@@ -598,7 +598,7 @@ int launch_bn_relu_apply(const void* x, const float* scale, const float* shift, 
 
 // dx = scale * (g - coef1 - xhat * coef2),  g = dy * [x*scale+shift > 0],  xhat = (x - mean) * rstd
 template <typename T, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : 4))
 bn_relu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                          const float* __restrict__ rstd, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ coef1,
@@ -609,15 +609,16 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
     const int c = (blockIdx.y * g.cvb + cv) * V;
     const int t = blockIdx.z;
     if (r >= g.rows_per_iter || c >= g.C) return;
-    float sc[V], sh[V], mu[V], rc2[V], c1[V];
+    // dx = scale * (g - c1 - (x - mean) * rstd * c2)  =  scale * g + ka * x + kb   (g = dy where ReLU is active)
+    float sc[V], sh[V], ka[V], kb[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const int ps = t * tstride + c + j, pc = t * g.C + c + j;
         sc[j] = __ldg(scale + ps);
         sh[j] = __ldg(shift + ps);
-        mu[j] = __ldg(mean + ps);
-        rc2[j] = __ldg(rstd + ps) * __ldg(coef2 + pc);
-        c1[j] = __ldg(coef1 + pc);
+        const float rc2 = __ldg(rstd + ps) * __ldg(coef2 + pc);
+        ka[j] = -sc[j] * rc2;
+        kb[j] = sc[j] * (rc2 * __ldg(mean + ps) - __ldg(coef1 + pc));
     }
     const long long p_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
     long long p_end = p_begin + g.rows_per_block;
@@ -631,7 +632,7 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
         for (int j = 0; j < V; ++j) {
             const float yv = fmaf(fx[j], sc[j], sh[j]);
             const float gq = yv > 0.f ? fd[j] : 0.f;
-            fd[j] = sc[j] * (gq - c1[j] - (fx[j] - mu[j]) * rc2[j]);
+            fd[j] = fmaf(sc[j], gq, fmaf(ka[j], fx[j], kb[j]));
         }
         stv<T, V>(dx + off, fd);
     };

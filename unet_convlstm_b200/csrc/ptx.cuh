@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz: far beyond any legitimate wait
-            if (err_flag) atomicExch(err_flag, tag);
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = tag;
             __threadfence_system();
             asm volatile("trap;");
         }

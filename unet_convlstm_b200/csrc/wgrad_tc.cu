@@ -128,7 +128,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches use the uniform datapath
     const int lane = threadIdx.x & 31;
     const int total_units = p.out_tiles * p.splits;
     // A operand (M = 128): stacked -> source boxes, normal -> dz boxes
@@ -168,13 +168,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
-    if (warp == 0) {
-        // =================================== TMA producer ===================================
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // =================================== TMA producers ==================================
         // The warp runs converged and ONE elected lane (elect.sync) issues every copy of a stage in one
         // straight-line block of UTMALDGs; under a divergent per-lane guard ptxas wraps each copy in an
         // ELECT/branch loop.  All coordinates are warp-uniform: the first tap of every group is
         // decoded once per unit (registers, the group loop is unrolled), the pixel-block coordinates
         // are carried by nested counters (no divisions in the loop).
+        //
+        // THREE producer warps share the issue work (profiles/r01_ncu_wgrad_producer_bound.txt: with one
+        // producer the 11 copies per 64-pixel block of the 64-channel layers cost ~2500 cycles of issue
+        // against ~1000 cycles of MMA): the tap groups of a block are dealt round-robin, producer 0 also
+        // loads the dz boxes.  Every producer walks the same stage sequence (sv, pv), waits for every
+        // stage to be free and fills the stages of its own groups.
+        constexpr int NPROD = 3;
+        const int pid = warp == 0 ? 0 : warp - 1;
         constexpr int MAX_GU = Cfg::MAX_GU;
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0;
@@ -204,24 +212,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             for (int rb = rb_begin; rb < rb_end; ++rb) {
                 const int w0 = wt * p.Wt, h0 = ht * p.Ht, b0 = bt * p.Bt;
                 // shared operand: the dz box(es) of this pixel block
-                mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 500 + ss);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(sfull(ss), s_tx);
-                    uint32_t dst = s_base + ss * Cfg::S_BYTES;
-                    int sc = u.s0;
-                    for (int i = 0; i < boxesS; ++i, dst += boxS_bytes, sc += cwS)
-                        tma_load_5d(dst, &tm_dz, sfull(ss), sc, w0, h0, b0, t);
-                }
-                __syncwarp();
-                if (++ss == SS) {
-                    ss = 0;
-                    ps ^= 1u;
+                if (pid == 0) {
+                    mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 500 + ss);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(sfull(ss), s_tx);
+                        uint32_t dst = s_base + ss * Cfg::S_BYTES;
+                        int sc = u.s0;
+                        for (int i = 0; i < boxesS; ++i, dst += boxS_bytes, sc += cwS)
+                            tma_load_5d(dst, &tm_dz, sfull(ss), sc, w0, h0, b0, t);
+                    }
+                    __syncwarp();
+                    if (++ss == SS) {
+                        ss = 0;
+                        ps ^= 1u;
+                    }
                 }
                 // varying operand: one stage per tap group
 #pragma unroll
                 for (int g = 0; g < MAX_GU; ++g) {
                     if (g < u.ngr) {
+                        // every producer waits for every stage, also those it does not fill: a parity
+                        // wait is only meaningful within one lap of the ring, so nobody may run ahead
                         mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
+                        if (g % NPROD == pid) {
                         if (elect_one()) {
                             const uint32_t fb = vfull(sv);
                             mbar_arrive_expect_tx(fb, v_tx);
@@ -247,6 +260,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                             }
                         }
                         __syncwarp();
+                        }
                         if (++sv == SV) {
                             sv = 0;
                             pv ^= 1u;
