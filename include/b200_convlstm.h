@@ -69,6 +69,20 @@ int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all, int Ch, in
                              const void* wpacked, const float* bias_packed, float* c_all, void* gates,
                              int have_h0, int ksize, void* stream);
 
+/* Whole-sequence BPTT data path of one ConvLSTM layer -- the autograd of the t-loop of ConvLSTM.forward
+ * (unet.py:52-57) -- as ONE timestep-persistent cooperative kernel running t = T-1 .. 0.  Step t is the
+ * data-gradient convolution of dz_t (wd_packed: bf16 [k*k flipped][Cin+Ch][4*Ch]) into [dx_t ; dh_{t-1}];
+ * the dh columns never leave the epilogue registers: they are added to the upstream dh_seq[t-1] and go
+ * through the gate-gradient math of step t-1 (autograd of unet.py:30-35), which writes dz_{t-1} (the next
+ * step's GEMM operand) and dL/dc_{t-2}.  dz_all: bf16 [T][P][4*Ch] (i|f|g|o), slot T-1 filled by the caller
+ * (b200_lstm_gates_bwd), the other slots here -- afterwards it is the dz operand of the weight gradient.
+ * gates: bf16 [T][P][4][Ch]; c_all: fp32 [T+1][P][Ch]; dh_seq: bf16 [T][P][Ch] or NULL; dc_buf: fp32
+ * [2][P][Ch], slot (T-1)&1 filled by the caller, slot 0 holds dL/dc_{-1} on return; dx_seq: bf16
+ * [T][P][Cin] or NULL (not needed); dh0: bf16 [P][Ch] or NULL (gradient of the initial hidden state). */
+int b200_convlstm_seq_bwd_tc(void* dz_all, const void* wd_packed, const void* gates, const float* c_all,
+                             const void* dh_seq, float* dc_buf, void* dx_seq, void* dh0, int Cin, int Ch,
+                             int T, int B, int H, int W, int have_h0, int ksize, void* stream);
+
 /* Weight gradient of a convolution, summed over all T*B images (autograd of nn.Conv2d, unet.py:19
  * and :70-71; for the ConvLSTM this is the BPTT sum over timesteps):
  *   dw[tap][n][koff + k] += sum_{t,p} dz[t,p,n] * src[t, p+tap, k]

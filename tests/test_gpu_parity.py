@@ -547,3 +547,57 @@ def test_wgrad_tc_long_reduction_multi_producer():
     torch.cuda.synchronize()
     assert _lib.lib().b200_device_error() == 0
     assert rel(_np(dw), _np(ref)) < 1e-4
+
+
+@pytest.mark.parametrize("T,B,H,W,Cin,Ch,have_h0,need_dx,with_dh,with_dc", [
+    (5, 8, 4, 4, 256, 256, False, True, True, False),    # bottleneck-like, zero initial state
+    (4, 2, 16, 16, 64, 64, True, True, True, True),      # carried state: dh0 / dc0 are produced
+    (3, 64, 8, 8, 128, 128, True, False, True, False),   # input does not need a gradient: dx tiles skipped
+    (4, 3, 16, 16, 32, 64, False, True, True, True),     # Cin != Ch, N tile straddles the dx | dh boundary
+    (2, 2, 16, 16, 64, 64, False, True, False, True),    # only the final cell state is used downstream
+])
+def test_lstm_fused_bptt_matches_stepwise(T, B, H, W, Cin, Ch, have_h0, need_dx, with_dh, with_dc):
+    """The timestep-persistent fused BPTT kernel (dgrad conv with the gate gradients of the previous step in
+    its epilogue) against the per-step path (b200_lstm_gates_bwd + b200_conv_tc_fwd per timestep): the only
+    arithmetic difference is that dh_{t-1} is no longer rounded to bf16 between the two kernels."""
+    from unet_convlstm_b200 import functional as Fn, ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    bf = torch.bfloat16
+    w = (torch.randn(4 * Ch, Cin + Ch, 3, 3, device="cuda", generator=g) / (9 * (Cin + Ch)) ** 0.5).requires_grad_(True)
+    b = (torch.randn(4 * Ch, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    x0 = torch.randn(T, B, H, W, Cin, device="cuda", generator=g).to(bf)
+    h0v = torch.randn(B, H, W, Ch, device="cuda", generator=g).to(bf)
+    c0v = torch.randn(B, H, W, Ch, device="cuda", generator=g)
+    dh_up = torch.randn(T, B, H, W, Ch, device="cuda", generator=g).to(bf)
+    dc_up = torch.randn(B, H, W, Ch, device="cuda", generator=g)
+    res = []
+    old = ops.FUSED_BPTT
+    try:
+        for persistent in (False, True):
+            ops.FUSED_BPTT = persistent
+            # poison the caching allocator's free blocks: an output element the kernel forgets to write must
+            # not inherit the right value from the previous pass of this loop
+            junk = torch.full((256 << 20,), float("nan"), device="cuda")
+            del junk
+            x = x0.clone().requires_grad_(need_dx)
+            h0 = h0v.clone().requires_grad_(True) if have_h0 else None
+            c0 = c0v.clone().requires_grad_(True) if have_h0 else None
+            w.grad = b.grad = None
+            h_seq, c_T = Fn.ConvLSTMSeq.apply(x, h0, c0, w, b, Fn.WeightCache())
+            loss = 0.0
+            if with_dh:
+                loss = loss + (h_seq.float() * dh_up.float()).sum()
+            if with_dc:
+                loss = loss + (c_T * dc_up).sum()
+            loss.backward()
+            torch.cuda.synchronize()
+            res.append({"dx": x.grad if need_dx else None, "dh0": h0.grad if have_h0 else None,
+                        "dc0": c0.grad if have_h0 else None, "dw": w.grad.clone(), "db": b.grad.clone()})
+    finally:
+        ops.FUSED_BPTT = old
+    for k in res[0]:
+        a, f = res[0][k], res[1][k]
+        assert (a is None) == (f is None), k
+        if a is not None:
+            assert torch.isfinite(f.float()).all(), k
+            assert rel2(_np(f), _np(a)) < 6e-3, (k, rel2(_np(f), _np(a)))

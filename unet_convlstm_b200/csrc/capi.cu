@@ -137,6 +137,31 @@ extern "C" int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all,
     return launch_convlstm_seq_tc(x_seq, h_all, wpacked, p, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int b200_convlstm_seq_bwd_tc(void* dz_all, const void* wd_packed, const void* gates, const float* c_all,
+                                        const void* dh_seq, float* dc_buf, void* dx_seq, void* dh0, int Cin, int Ch,
+                                        int T, int B, int H, int W, int have_h0, int ksize, void* stream) {
+    if (!dz_all || !wd_packed || !gates || !c_all || !dc_buf || Cin <= 0 || Ch <= 0 || T <= 0 || (ksize & 1) == 0) {
+        set_last_error("b200_convlstm_seq_bwd_tc: bad arguments");
+        return B200_ERR_ARG;
+    }
+    ConvTcParams p = {};
+    p.T = 1; p.B = B; p.H = H; p.W = W;
+    p.C0 = 4 * Ch; p.C1 = 0;
+    p.N = Cin + Ch; p.ksize = ksize;
+    p.seq_T = T;
+    p.seq_have_h0 = have_h0;
+    p.bwd_Cin = Cin; p.bwd_Ch = Ch;
+    p.bwd_P = static_cast<long long>(B) * H * W;
+    p.bwd_gates = static_cast<const __nv_bfloat16*>(gates);
+    p.bwd_c_all = c_all;
+    p.bwd_dh_seq = static_cast<const __nv_bfloat16*>(dh_seq);
+    p.bwd_dc = dc_buf;
+    p.bwd_dz_all = static_cast<__nv_bfloat16*>(dz_all);
+    p.bwd_dx_seq = static_cast<__nv_bfloat16*>(dx_seq);
+    p.bwd_dh0 = static_cast<__nv_bfloat16*>(dh0);
+    return launch_convlstm_seq_bwd_tc(wd_packed, p, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
                              int ksize, float* dw, long long ldk, int koff, void* stream) {
     if (!dz || !src || !dw || Nz <= 0 || Csrc <= 0 || (ksize & 1) == 0 || koff < 0 || koff + Csrc > ldk) {

@@ -26,11 +26,20 @@
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 static constexpr int BLOCK_M = 128;
-static constexpr int NUM_THREADS = 256;
 static constexpr int EPI_WARP0 = 4;
+// Epilogue warps: 4 (one per TMEM lane quarter) for the plain store and the forward cell update; 8 for the
+// BPTT epilogue, whose per-element operand loads (gates, c, dc, dh: ~34 bytes) are latency bound -- two
+// warps share a lane quarter and split the columns of the tile.
+template <int EPI>
+struct EpiCfg {
+    static constexpr int WARPS = (EPI == EPI_LSTM_BWD) ? 8 : 4;
+    static constexpr int THREADS = (EPI_WARP0 + WARPS) * 32;
+};
 
 template <int BLOCK_N>
 struct TcCfg {
@@ -86,7 +95,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
 }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                const __grid_constant__ CUtensorMap tm_b, const ConvTcParams p) {
     using Cfg = TcCfg<BLOCK_N>;
@@ -119,6 +128,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     // c_t stay in the L2-resident state buffers and a grid-wide counter separates the steps
     const bool seq = p.seq_T > 0;
     const int nsteps = seq ? p.seq_T : 1;
+    // BPTT runs the sequence backwards; a tile whose columns nobody needs is skipped by all three roles
+    // (dx columns without a dx_seq buffer; dh columns at t = 0 without a dh0 buffer)
+    auto step_t = [&](int step) { return (EPI == EPI_LSTM_BWD) ? p.seq_T - 1 - step : step; };
+    // i-th tile of this CTA: -2 = no more tiles, -1 = nothing in this slot.  Default: blockIdx.x + i * grid.
+    // BPTT (p.bwd_alternate): the N tiles split into a dh half (heavy gate-gradient epilogue) and a dx half
+    // (plain store); a CTA alternates between them, heavy first, so that a heavy epilogue always overlaps
+    // the main loop of a light tile and the last tile of a step is a light one.
+    const int half_tiles = (p.num_n_tiles >> 1) * p.num_m_tiles;
+    const int alt_iters = 2 * ((half_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
+    auto tile_at = [&](int i) {
+        if (EPI == EPI_LSTM_BWD && p.bwd_alternate) {
+            if (i >= alt_iters) return -2;
+            const int u = (i >> 1) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+            if (u >= half_tiles) return -1;
+            return ((i & 1) ? 0 : half_tiles) + u;
+        }
+        const int t = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        return t < total_tiles ? t : -2;
+    };
+    auto tile_active = [&](int t, int n0) {
+        if constexpr (EPI != EPI_LSTM_BWD) return true;
+        if (n0 + BLOCK_N <= p.bwd_Cin) return p.bwd_dx_seq != nullptr;
+        if (n0 >= p.bwd_Cin) return t > 0 || p.bwd_dh0 != nullptr;
+        return true;
+    };
     const uint32_t a_bytes = BLOCK_M * p.kc * 2;
     const uint32_t b_bytes = BLOCK_N * p.kc * 2;
 
@@ -134,7 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), EpiCfg<EPI>::WARPS);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -166,9 +200,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 __syncwarp();
                 fence_proxy_async_all();  // every lane: whichever one is elected issues the TMA reads
             }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int ti = 0;; ++ti) {
+                const int tile = tile_at(ti);
+                if (tile == -2) break;
+                if (tile < 0) continue;
                 TileCoord tc = decode_tile(p, tile, BLOCK_N);
-                if (seq) tc.t = step;
+                if (seq) tc.t = step_t(step);
+                if (!tile_active(tc.t, tc.n0)) continue;
                 int ky = 0, kx = 0;
                 for (int tap = 0; tap < taps; ++tap) {
                     const int cw = tc.w0 + kx - p.pad, chh = tc.h0 + ky - p.pad;
@@ -219,7 +257,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         constexpr uint32_t STAGE_LO = Cfg::STAGE_BYTES >> 4, B_LO = Cfg::A_BYTES >> 4;
         for (int step = 0; step < nsteps; ++step) {
             const int num_kb_t = (seq && step == 0 && !p.seq_have_h0) ? taps * chunks0 : num_kb;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int ti = 0;; ++ti) {
+                const int tile = tile_at(ti);
+                if (tile == -2) break;
+                if (tile < 0) continue;
+                if constexpr (EPI == EPI_LSTM_BWD) {
+                    if (!tile_active(step_t(step), (tile / p.num_m_tiles) * BLOCK_N)) continue;
+                }
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -262,7 +306,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
     } else if (warp >= EPI_WARP0) {
         // =================================== epilogue =======================================
-        const int q = static_cast<int>(threadIdx.x >> 5) - EPI_WARP0;  // TMEM lane quarter == warp % 4 (vector-register copy)
+        const int ew = static_cast<int>(threadIdx.x >> 5) - EPI_WARP0;  // epilogue warp (vector-register copy)
+        const int q = ew & 3;             // TMEM lane quarter == warp % 4
+        const int chalf = ew >> 2;        // column half of the tile (always 0 with 4 epilogue warps)
+        constexpr int C16_PER_WARP = BLOCK_N / 16 / (EpiCfg<EPI>::WARPS / 4);
         const int r = q * 32 + lane;     // row of the M tile
         const int wi = r % p.Wt;
         const int hi = (r / p.Wt) % p.Ht;
@@ -291,9 +338,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         if (do_stats) stat_flush();  // zeroes the buffer (stat_t < 0: nothing is added)
         for (int step = 0; step < nsteps; ++step) {
         const bool zero_state = seq && step == 0 && !p.seq_have_h0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ti = 0;; ++ti) {
+                const int tile = tile_at(ti);
+                if (tile == -2) break;
+                if (tile < 0) continue;
             TileCoord tc = decode_tile(p, tile, BLOCK_N);
-            if (seq) tc.t = step;
+            if (seq) tc.t = step_t(step);
+            if (!tile_active(tc.t, tc.n0)) continue;
             if (do_stats && (tc.t != stat_t || tc.n0 != stat_n0)) {
                 if (stat_t >= 0) stat_flush();
                 stat_t = tc.t;
@@ -302,6 +353,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             const bool valid = (tc.h0 + hi < p.H) && (tc.b0 + bi < p.B);
             const long long pix =
                 ((static_cast<long long>(tc.t) * p.B + tc.b0 + bi) * p.H + tc.h0 + hi) * p.W + tc.w0 + wi;
+            if constexpr (EPI == EPI_LSTM_BWD) {
+                // The gate-gradient operands of this tile (gates, c, dc, upstream dh: ~34 bytes per element,
+                // cold in HBM) are known before the accumulator is: pull them into L2 while the main loop of
+                // the tile is still running, so the epilogue's dependent loads are L2 hits.
+                const int cb = max(tc.n0, p.bwd_Cin) - p.bwd_Cin;
+                const int ce = min(tc.n0 + BLOCK_N, p.N) - p.bwd_Cin;
+                if (valid && ce > cb && tc.t > 0) {
+                    const int Ch = p.bwd_Ch;
+                    const long long pin = pix - static_cast<long long>(tc.t) * p.bwd_P;
+                    const long long sp = static_cast<long long>(tc.t - 1) * p.bwd_P + pin;
+                    const char* gr = reinterpret_cast<const char*>(p.bwd_gates + sp * (4LL * Ch) + cb);
+                    const char* c0 = reinterpret_cast<const char*>(p.bwd_c_all + sp * Ch + cb);
+                    const char* c1 = reinterpret_cast<const char*>(p.bwd_c_all + (sp + p.bwd_P) * Ch + cb);
+                    const char* dcp = reinterpret_cast<const char*>(
+                        p.bwd_dc + (static_cast<long long>(tc.t & 1) * p.bwd_P + pin) * Ch + cb);
+                    const int nb2 = (ce - cb) * 2, nb4 = (ce - cb) * 4;
+                    for (int o = 0; o < nb2; o += 128) {
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) prefetch_l2(gr + gq * Ch * 2 + o);
+                        if (p.bwd_dh_seq) prefetch_l2(reinterpret_cast<const char*>(p.bwd_dh_seq + sp * Ch + cb) + o);
+                    }
+                    for (int o = 0; o < nb4; o += 128) {
+                        if (tc.t > 1 || p.seq_have_h0) prefetch_l2(c0 + o);
+                        prefetch_l2(c1 + o);
+                        prefetch_l2(dcp + o);
+                    }
+                }
+            }
             mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
@@ -371,6 +450,103 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                                               pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
                         }
                     }
+                }
+            } else if constexpr (EPI == EPI_LSTM_BWD) {
+                // ---- BPTT step: [dx_t ; dh_{t-1}] columns; the dh columns feed the gate gradients of
+                //      step t-1 (autograd of reference train/unet.py:30-35) without leaving the registers ----
+                const int Cin = p.bwd_Cin, Ch = p.bwd_Ch;
+                const long long pin = pix - static_cast<long long>(tc.t) * p.bwd_P;  // pixel within the step
+                const int tp = tc.t - 1;                                              // gate-gradient step
+#pragma unroll 1
+                for (int c16 = chalf * C16_PER_WARP; c16 < (chalf + 1) * C16_PER_WARP; ++c16) {
+                    const int ncol = tc.n0 + c16 * 16;
+                    if (ncol >= p.N) break;  // warp-uniform
+                    if (ncol < Cin ? p.bwd_dx_seq == nullptr : (tp < 0 && p.bwd_dh0 == nullptr)) continue;
+                    uint32_t v[16];
+                    tmem_ld16(t_row + c16 * 16, v);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    auto st16 = [](__nv_bfloat16* dst, const float* s) {
+                        uint4* o = reinterpret_cast<uint4*>(dst);
+                        o[0] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]),
+                                          pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+                        o[1] = make_uint4(pack_bf16x2(s[8], s[9]), pack_bf16x2(s[10], s[11]),
+                                          pack_bf16x2(s[12], s[13]), pack_bf16x2(s[14], s[15]));
+                    };
+                    auto ld16 = [](const __nv_bfloat16* src, float* d) {
+                        const uint4* q4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const uint4 u = q4[h2];
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                d[8 * h2 + 2 * j] = __uint_as_float(w[j] << 16);
+                                d[8 * h2 + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+                            }
+                        }
+                    };
+                    auto ld16f = [](const float* src, float* d) {
+                        const float4* q4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 u = q4[j];
+                            d[4 * j] = u.x; d[4 * j + 1] = u.y; d[4 * j + 2] = u.z; d[4 * j + 3] = u.w;
+                        }
+                    };
+                    float dh[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dh[j] = __uint_as_float(v[j]);
+                    if (ncol < Cin) {
+                        st16(p.bwd_dx_seq + pix * Cin + ncol, dh);
+                        continue;
+                    }
+                    const int ch = ncol - Cin;
+                    if (tp < 0) {
+                        st16(p.bwd_dh0 + pin * Ch + ch, dh);  // dL/dh_{-1}: gradient of the initial state
+                        continue;
+                    }
+                    const long long sp = static_cast<long long>(tp) * p.bwd_P + pin;  // (step t-1, pixel)
+                    if (p.bwd_dh_seq) {
+                        float up[16];
+                        ld16(p.bwd_dh_seq + sp * Ch + ch, up);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dh[j] += up[j];
+                    }
+                    float gi[16], gf[16], gg[16], go[16], cp[16], cn[16], dc[16];
+                    const __nv_bfloat16* gr = p.bwd_gates + sp * (4LL * Ch) + ch;
+                    ld16(gr, gi);
+                    ld16(gr + Ch, gf);
+                    ld16(gr + 2 * Ch, gg);
+                    ld16(gr + 3 * Ch, go);
+                    if (tp > 0 || p.seq_have_h0) {
+                        ld16f(p.bwd_c_all + sp * Ch + ch, cp);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cp[j] = 0.f;  // zero initial state (unet.py:23-25)
+                    }
+                    ld16f(p.bwd_c_all + (sp + p.bwd_P) * Ch + ch, cn);
+                    ld16f(p.bwd_dc + (static_cast<long long>(tc.t & 1) * p.bwd_P + pin) * Ch + ch, dc);
+                    float zi[16], zf[16], zg[16], zo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float tch = fast_tanh(cn[j]);
+                        const float d_o = dh[j] * tch;
+                        const float d_c = fmaf(dh[j] * go[j], 1.f - tch * tch, dc[j]);
+                        zi[j] = d_c * gg[j] * gi[j] * (1.f - gi[j]);
+                        zf[j] = d_c * cp[j] * gf[j] * (1.f - gf[j]);
+                        zg[j] = d_c * gi[j] * (1.f - gg[j] * gg[j]);
+                        zo[j] = d_o * go[j] * (1.f - go[j]);
+                        dc[j] = d_c * gf[j];
+                    }
+                    __nv_bfloat16* zr = p.bwd_dz_all + sp * (4LL * Ch) + ch;
+                    st16(zr, zi);
+                    st16(zr + Ch, zf);
+                    st16(zr + 2 * Ch, zg);
+                    st16(zr + 3 * Ch, zo);
+                    float4* dco = reinterpret_cast<float4*>(p.bwd_dc + (static_cast<long long>(tp & 1) * p.bwd_P + pin) * Ch + ch);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dco[j] = make_float4(dc[4 * j], dc[4 * j + 1], dc[4 * j + 2], dc[4 * j + 3]);
                 }
             } else {
                 // ---- fused LSTM cell update (reference train/unet.py:29-35) ----
@@ -465,8 +641,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
         if (seq && step + 1 < nsteps) {
             // publish h_t / c_t of this CTA's tiles, then signal the grid-wide step counter
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EpiCfg<EPI>::WARPS * 32) : "memory");
             if (threadIdx.x == EPI_WARP0 * 32) {
+                // A CTA without an active tile in this step has not been held back by its producer: it must
+                // not signal step s before every CTA has finished step s-1 (the counter only counts arrivals)
+                if (step > 0) grid_wait(p.sync_ctr, gridDim.x * step, p.err_flag);
                 __threadfence();
                 atomicAdd(p.sync_ctr, 1u);
             }
@@ -517,10 +696,10 @@ static int launch_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
         void* args[] = {const_cast<CUtensorMap*>(&ta0), const_cast<CUtensorMap*>(&ta1),
                         const_cast<CUtensorMap*>(&tb), const_cast<ConvTcParams*>(&p)};
         B200_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid),
-                                                    dim3(NUM_THREADS), args, Cfg::SMEM_BYTES, stream));
+                                                    dim3(EpiCfg<EPI>::THREADS), args, Cfg::SMEM_BYTES, stream));
         return B200_OK;
     }
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta0, ta1, tb, p);
+    kern<<<grid, EpiCfg<EPI>::THREADS, Cfg::SMEM_BYTES, stream>>>(ta0, ta1, tb, p);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200_OK;
 }
@@ -533,6 +712,19 @@ int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpa
         return B200_ERR_ARG;
     }
     return launch_conv_tc(x_seq, h_all, wpacked, p, EPI_LSTM, stream);
+}
+
+int launch_convlstm_seq_bwd_tc(const void* wd_packed, ConvTcParams p, cudaStream_t stream) {
+    p.sync_ctr = device_sync_counter();
+    if (!p.sync_ctr || p.seq_T <= 0 || !p.bwd_dz_all || !p.bwd_gates || !p.bwd_c_all || !p.bwd_dc) {
+        set_last_error("convlstm_seq_bwd_tc: missing buffers / bad sequence length");
+        return B200_ERR_ARG;
+    }
+    if (p.bwd_Cin % 16 != 0 || p.bwd_Ch % 16 != 0) {
+        set_last_error("convlstm_seq_bwd_tc: Cin=%d Ch=%d must be multiples of 16", p.bwd_Cin, p.bwd_Ch);
+        return B200_ERR_SHAPE;
+    }
+    return launch_conv_tc(p.bwd_dz_all, nullptr, wd_packed, p, EPI_LSTM_BWD, stream);
 }
 
 int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi,
@@ -569,6 +761,12 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
     if (p.seq_T > 0) p.T = 1;  // tiles of ONE step; the kernel iterates over the steps itself
     p.num_m_tiles = p.T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
     p.num_n_tiles = (p.N + block_n - 1) / block_n;
+    static const bool alt_ok = [] {
+        const char* e = getenv("B200_BWD_ALTERNATE");  // developer switch (A/B of the tile order)
+        return !e || atoi(e) != 0;
+    }();
+    p.bwd_alternate = (alt_ok && epi == EPI_LSTM_BWD && (p.num_n_tiles & 1) == 0 &&
+                       p.bwd_Cin == (p.num_n_tiles / 2) * block_n) ? 1 : 0;
     p.pad = p.ksize / 2;
     p.err_flag = device_error_flag();
 
@@ -590,6 +788,13 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
             case 256: return launch_impl<256, EPI_LSTM>(ta0, ta1, tb, p, stream);
             case 128: return launch_impl<128, EPI_LSTM>(ta0, ta1, tb, p, stream);
             default: return launch_impl<64, EPI_LSTM>(ta0, ta1, tb, p, stream);
+        }
+    }
+    if (epi == EPI_LSTM_BWD) {
+        switch (block_n) {
+            case 256: return launch_impl<256, EPI_LSTM_BWD>(ta0, ta1, tb, p, stream);
+            case 128: return launch_impl<128, EPI_LSTM_BWD>(ta0, ta1, tb, p, stream);
+            default: return launch_impl<64, EPI_LSTM_BWD>(ta0, ta1, tb, p, stream);
         }
     }
     switch (block_n) {

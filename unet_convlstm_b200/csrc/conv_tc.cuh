@@ -7,6 +7,8 @@ namespace b200 {
 enum ConvEpilogue : int {
     EPI_STORE = 0,  // out = acc (+bias) (+relu) -> bf16 / fp32, optionally split over two tensors
     EPI_LSTM = 1,   // gate-interleaved N tile: sigma/tanh gate math + c/h update (unet.py:29-35)
+    EPI_LSTM_BWD = 2,  // BPTT: data-gradient conv of dz_t -> [dx_t ; dh_{t-1}], the dh columns go straight
+                       // into the gate-gradient math of step t-1 (autograd of unet.py:30-35) -> dz_{t-1}
 };
 
 struct ConvTcParams {
@@ -44,6 +46,17 @@ struct ConvTcParams {
     // slot 0 / slot 1 / slot 1 / step 0 of their sequence buffers
     int seq_T;
     int seq_have_h0;
+    // EPI_LSTM_BWD (always timestep-persistent, t = seq_T-1 .. 0).  N = Cin + Ch, source 0 = dz_all.
+    int bwd_Cin, bwd_Ch;
+    int bwd_alternate;               // set by the launcher: N tiles split evenly into a dx half and a dh half
+    long long bwd_P;                 // pixels per timestep (B*H*W)
+    const __nv_bfloat16* bwd_gates;  // [T][P][4][Ch] activated i,f,g,o
+    const float* bwd_c_all;          // [T+1][P][Ch]
+    const __nv_bfloat16* bwd_dh_seq; // [T][P][Ch] upstream dL/dh_t or nullptr
+    float* bwd_dc;                   // [2][P][Ch] ping-pong: slot (t & 1) holds dL/dc_{t-1} produced at step t
+    __nv_bfloat16* bwd_dz_all;       // [T][P][4*Ch] (i|f|g|o): slot T-1 is filled by the caller, the rest here
+    __nv_bfloat16* bwd_dx_seq;       // [T][P][Cin] or nullptr
+    __nv_bfloat16* bwd_dh0;          // [P][Ch] dL/dh_{-1} or nullptr
     unsigned* sync_ctr;
     int* err_flag;
 };
@@ -55,6 +68,9 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
 // Whole-sequence forward of one ConvLSTM layer in ONE cooperative launch (see ConvTcParams::seq_T).
 int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpacked, ConvTcParams p,
                            cudaStream_t stream);
+
+// Whole-sequence BPTT data path of one ConvLSTM layer in ONE cooperative launch (EPI_LSTM_BWD).
+int launch_convlstm_seq_bwd_tc(const void* wd_packed, ConvTcParams p, cudaStream_t stream);
 
 // conv_halo.cu: 3x3 convolution with the activation tile loaded once per output tile (narrow layers).
 bool conv_halo_supported(int IMG, int H, int W, int C0, int C1, int N, int ksize);

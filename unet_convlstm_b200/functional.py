@@ -295,6 +295,17 @@ class ConvLSTMSeq(torch.autograd.Function):
         dz_all = torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
         need_dx = ctx.needs_input_grad[0]
         dx_seq = torch.empty_like(x_seq) if need_dx else None
+        if ops.lstm_seq_bwd_ok(x_seq, Ch):
+            # fused timestep-persistent BPTT: the gate gradients of the last step, then ONE cooperative
+            # launch for t = T-1 .. 0 (dgrad conv of dz_t with the gate gradients of step t-1 in its epilogue)
+            dc_buf = torch.empty((2, B, H, W, Ch), device=dev, dtype=torch.float32)
+            want_dh0 = ctx.have_h0 and ctx.needs_input_grad[1]
+            dh0 = torch.empty((B, H, W, Ch), device=dev, dtype=dt) if want_dh0 else None
+            ops.lstm_gates_bwd(gates[T - 1], c_all[T - 1], c_all[T], None if dh_seq is None else dh_seq[T - 1], None,
+                               dc_next, dz_all[T - 1], dc_buf[(T - 1) & 1])
+            ops.lstm_seq_bwd_fused(dz_all, wd, gates, c_all, dh_seq, dc_buf, dx_seq, dh0, Cin, ctx.have_h0, ks)
+            dc0 = dc_buf[0] if (ctx.have_h0 and ctx.needs_input_grad[2]) else None
+            return ConvLSTMSeq._finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0)
         dx_scratch = None if need_dx else torch.empty_like(x_seq[0])
         dh_rec = [torch.empty((B, H, W, Ch), device=dev, dtype=dt) for _ in range(2)]
         dc_buf = [torch.empty((B, H, W, Ch), device=dev, dtype=torch.float32) for _ in range(2)]
@@ -313,8 +324,21 @@ class ConvLSTMSeq(torch.autograd.Function):
                 # only the x columns of the data gradient are needed at t = 0 with a zero initial state
                 ops.conv_fwd(dz_all[t].unsqueeze(0), None, wd[:, :Cin, :].contiguous(), None, ks,
                              dx_seq[t].unsqueeze(0))
-        # weight / bias gradients: one reduction over the whole sequence
-        dwp = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=dev, dtype=torch.float32)
+        dh0 = dc0 = None
+        if ctx.have_h0:
+            if ctx.needs_input_grad[1]:
+                dh0 = dh_b
+            if ctx.needs_input_grad[2]:
+                dc0 = dc_next
+        return ConvLSTMSeq._finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0)
+
+    @staticmethod
+    def _finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0):
+        """Weight / bias gradients: one reduction over the whole sequence (K = T*B*H*W)."""
+        T, B, H, W, Cin = x_seq.shape
+        Ch = weight.shape[0] // 4
+        ks = weight.shape[2]
+        dwp = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=x_seq.device, dtype=torch.float32)
         ops.conv_wgrad(dz_all, x_seq, ks, dwp, 0)
         if ctx.have_h0:
             ops.conv_wgrad(dz_all, h_all[:T], ks, dwp, Cin)
@@ -322,11 +346,5 @@ class ConvLSTMSeq(torch.autograd.Function):
             ops.conv_wgrad(dz_all[1:], h_all[1:T], ks, dwp, Cin)  # h_{-1} = 0 contributes nothing
         dweight = ops.unpack_conv_wgrad(dwp, Cin + Ch)
         dbias = ops.colsum(T * B * H * W, dz_all, 4 * Ch) if ctx.has_bias else None
-        dh0 = dc0 = None
-        if ctx.have_h0:
-            if ctx.needs_input_grad[1]:
-                dh0 = dh_b
-            if ctx.needs_input_grad[2]:
-                dc0 = dc_next
         ctx.h_all = ctx.c_all = ctx.gates = None
         return dx_seq, dh0, dc0, dweight, dbias, None

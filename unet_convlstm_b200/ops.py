@@ -375,6 +375,11 @@ FUSE_BN_STATS = os.environ.get("B200_FUSE_BN_STATS", "0") == "1"
 # One cooperative timestep-persistent launch per ConvLSTM layer (default) or one launch per timestep
 PERSISTENT_LSTM = os.environ.get("B200_PERSISTENT_LSTM", "1") != "0"
 
+# Fused timestep-persistent BPTT kernel (b200_convlstm_seq_bwd_tc) instead of per-step gate-gradient + dgrad
+# launches.  Opt-in: measured on B200 (profiles/r01_fused_bptt_measured.txt) the gate-gradient operand traffic
+# of the epilogue competes with the L2-bound main loop and the per-step pair of launches is 0-13 % faster.
+FUSED_BPTT = os.environ.get("B200_FUSED_BPTT", "0") == "1"
+
 # bench.py sets this to a list to time every fused cell launch with CUDA events on the launching stream:
 # entries are (start_event, end_event, algorithmic_flops)
 CELL_TIMER = None
@@ -415,6 +420,27 @@ def lstm_seq_fwd_fused(x_seq, h_all, c_all, wp_il, bias_il, gates, have_h0, ksiz
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         timer.append((e0, e1, fl))
+
+
+def lstm_seq_bwd_ok(x_seq, Ch) -> bool:
+    """Can the fused timestep-persistent BPTT kernel run this layer?"""
+    if x_seq.dtype != torch.bfloat16 or not PERSISTENT_LSTM or not FUSED_BPTT:
+        return False
+    T, B, H, W, Cin = x_seq.shape
+    if T < 2 or Cin % 16 or Ch % 16:
+        return False
+    return _lib.supported("b200_conv_tc_supported", B, H, W, 4 * Ch, 0, Cin + Ch, 0)
+
+
+def lstm_seq_bwd_fused(dz_all, wd, gates, c_all, dh_seq, dc_buf, dx_seq, dh0, Cin, have_h0, ksize):
+    """Steps T-1 .. 0 of BPTT in one cooperative launch: dgrad conv of dz_t with the gate gradients of step
+    t-1 in its epilogue (see include/b200_convlstm.h).  dz_all[T-1] and dc_buf[(T-1) & 1] must be filled."""
+    T, B, H, W, C4 = dz_all.shape
+    Ch = C4 // 4
+    fl = 2.0 * T * B * H * W * ksize * ksize * C4 * (Cin + Ch)
+    _lib.call("b200_convlstm_seq_bwd_tc", _p(dz_all), _p(wd), _p(gates), _p(c_all), _p(dh_seq), _p(dc_buf),
+              _p(dx_seq), _p(dh0), Cin, Ch, T, B, H, W, int(have_h0), ksize, _st(),
+              tag=f"Ch{Ch} {H}x{W} T{T}", work=(fl, None))
 
 
 def lstm_cell_fwd_unfused(x_t, h_prev, c_prev, wp, bias, c_next, h_next, gates, ksize, zbuf):
