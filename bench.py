@@ -64,7 +64,21 @@ def make_batch(B, T, S, seed):
                     ny = py + vy
                 px, py = int(nx), int(ny)
     X[:, :, 1, :, 1:] = X[:, :, 0, :, :-1]
-    return torch.from_numpy(X), torch.from_numpy(np.clip(Y, -1, 1))
+    M = (X[:, :, :1] > 0).astype(np.float32)  # "cloud mask": the pixels the target is defined on (unet.py:279)
+    return torch.from_numpy(X), torch.from_numpy(np.clip(Y, -1, 1)), torch.from_numpy(M)
+
+
+def loss_torch(y_pred, y, mask):
+    """The reference's training loss (main.py:28-72: weighted L1 + 0.005 x spatial-gradient loss, masked means)
+    written with torch operators -- the CPU reference arm's loss; the B200 arm uses the fused kernels of
+    unet_convlstm_b200.loss on the same formula (both pinned by tests/golden/loss_main_compute_loss.npz)."""
+    w = 1.0 + 4.0 * y.abs() ** 3
+    d = y_pred - y
+    l1 = (d.abs() * mask * w).sum() / ((mask * w).sum() + 1e-8)
+    dxe = d[..., :-1, 1:] - d[..., :-1, :-1]
+    dye = d[..., 1:, :-1] - d[..., :-1, :-1]
+    mc = mask[..., :-1, :-1]
+    return l1 + 0.005 * ((dxe.abs() + dye.abs()) * mc).sum() / (mc.sum() + 1e-8)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,13 +148,15 @@ def cpu_reference_run(args, steps, warmup, batch):
     sd = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).state_dict()
     p = TP.params_from_state_dict(sd, torch.float32)
     opt = torch.optim.AdamW([v for v in p.values() if v.requires_grad], lr=1e-3, weight_decay=1e-4)
-    x, y = make_batch(batch, args.seq_len, args.size, 1234)
+    x, y, mask = make_batch(batch, args.seq_len, args.size, 1234)
+    params = [v for v in p.values() if v.requires_grad]
 
     def step():
         opt.zero_grad(set_to_none=True)
         out, _ = TP.temporal_unet(p, x, None, training=True)
-        loss = ((torch.stack(out, dim=1) - y) ** 2).mean()
+        loss = loss_torch(torch.stack(out, dim=1), y, mask)
         loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
         return loss.item()
 
@@ -181,7 +197,8 @@ def workload_config(args, batch_per_step=None):
                     f"batch {args.batch} per GPU, base_ch {args.base_ch} + skip ConvLSTMs (BASELINE.json configs[1])",
         "batch_per_gpu": args.batch if batch_per_step is None else batch_per_step, "seq_len": args.seq_len,
         "image": args.size, "base_ch": args.base_ch, "use_skip_lstm": True, "precision": args.precision,
-        "step": "forward + backward + AdamW(fused) update; gradient all-reduce overlapped when N > 1",
+        "step": "the reference's training step (main.py:94-108): forward, compute_loss (weighted L1 + gradient loss, "
+                "masked), backward, clip_grad_norm_(1.0), AdamW(fused) update; gradient all-reduce overlapped when N > 1",
         "parallelism": f"dp{args.gpus}",
         "l2": "per-step working set (tens of GB of activations, 168 MB of inputs) far exceeds the 126 MB L2",
     }
@@ -214,18 +231,23 @@ def run_b200_arm(args, out):
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=use_graph)
     reducer = GradReducer(model.parameters()) if world > 1 else None
 
-    x_host, y_host = make_batch(args.batch, args.seq_len, args.size, 1234 + rank)
-    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
-    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    from unet_convlstm_b200.loss import compute_loss
+    x_host, y_host, m_host = make_batch(args.batch, args.seq_len, args.size, 1234 + rank)
+    x_host, y_host, m_host = x_host.pin_memory(), y_host.pin_memory(), m_host.pin_memory()
+    x_dev, y_dev, m_dev = x_host.to(dev), y_host.to(dev), m_host.to(dev)
+    params = [q for q in model.parameters() if q.requires_grad]
 
-    def step(x, y, with_opt=True):
+    def step(x, y, m, with_opt=True):
+        # the reference's training step (main.py:94-108): forward, compute_loss, backward, clip_grad_norm_(1.0),
+        # optimizer step
         opt.zero_grad(set_to_none=True)
         out, _ = model(x)
-        loss = ((torch.stack(out, dim=1) - y) ** 2).mean()
+        loss = compute_loss(torch.stack(out, dim=1), y, m)
         loss.backward()
         if reducer is not None:
             reducer.finish()
         if with_opt:
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
             opt.step()
         return loss
 
@@ -250,12 +272,12 @@ def run_b200_arm(args, out):
     if args.profile_steps:
         # for `ncu`: one warm-up step (packs weights, sizes the caching allocator) + N plain steps, no timing
         for _ in range(1 + args.profile_steps):
-            step(x_dev, y_dev)
+            step(x_dev, y_dev, m_dev)
         torch.cuda.synchronize()
         return
 
     for _ in range(args.warmup):
-        step(x_dev, y_dev)
+        step(x_dev, y_dev, m_dev)
 
     if args.breakdown:
         # one instrumented step: CUDA events around every C-ABI call (adds event overhead; the per-kernel
@@ -263,7 +285,7 @@ def run_b200_arm(args, out):
         _lib.TIMER = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step(x_dev, y_dev)
+        step(x_dev, y_dev, m_dev)
         e1.record()
         torch.cuda.synchronize()
         ev, _lib.TIMER = _lib.TIMER, None
@@ -293,7 +315,7 @@ def run_b200_arm(args, out):
     # ---- eager region: every launch from Python, CUDA events around each fused cell launch (roofline) ----
     ops.CELL_TIMER = []
     calls0 = _lib.kernel_launches()
-    ms_eager = timed(lambda: step(x_dev, y_dev), args.steps)
+    ms_eager = timed(lambda: step(x_dev, y_dev, m_dev), args.steps)
     launches = _lib.kernel_launches() - calls0
     cell_events, ops.CELL_TIMER = ops.CELL_TIMER, None
     torch.cuda.synchronize()
@@ -301,7 +323,7 @@ def run_b200_arm(args, out):
     cell_flops = [fl for _, _, fl in cell_events]
 
     # ---- fwd+bwd only (no optimizer), for the record --------------------------------------------
-    ms_fb = timed(lambda: step(x_dev, y_dev, with_opt=False), max(1, args.steps // 2))
+    ms_fb = timed(lambda: step(x_dev, y_dev, m_dev, with_opt=False), max(1, args.steps // 2))
     # ---- timed region 1: inputs resident in HBM = the eager region above; with --graph 1 the same step --
     #      same kernels, same order -- is captured once into a CUDA graph and replayed instead
     #      (unet_convlstm_b200.graph.GraphedTrainStep; single GPU only) ----
@@ -310,7 +332,7 @@ def run_b200_arm(args, out):
         from unet_convlstm_b200.graph import GraphedTrainStep
         opt.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()  # the graph keeps its own pool of activations (~60 GB at this workload)
-        gstep = GraphedTrainStep(model, opt, lambda out, y: ((torch.stack(out, dim=1) - y) ** 2).mean(),
+        gstep = GraphedTrainStep(model, opt, lambda out, y: compute_loss(torch.stack(out, dim=1), y, m_dev),
                                  x_dev, y_dev, warmup=1)
         for _ in range(2):
             gstep()
@@ -326,12 +348,12 @@ def run_b200_arm(args, out):
     pf = DevicePrefetcher(dev)
 
     def e2e_region(steps):
-        pf.start(x_host, y_host)
+        pf.start(x_host, y_host, m_host)
         for i in range(steps):
-            x, y = pf.get()
+            x, y, m = pf.get()
             if i + 1 < steps:
-                pf.start(x_host, y_host)
-            (gstep(x, y) if gstep is not None else step(x, y)).item()
+                pf.start(x_host, y_host, m_host)
+            (gstep(x, y) if gstep is not None else step(x, y, m)).item()
 
     e2e_region(2)
     ms_e2e = timed(lambda: e2e_region(args.steps), 1) / args.steps
@@ -362,7 +384,8 @@ def run_b200_arm(args, out):
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": world * args.batch / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": (x_host.numel() + y_host.numel() + m_host.numel()) * 4,
+                    "d2h_bytes_per_step": 4},
             "fwd_bwd_only": {"value": world * args.batch / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb},
             "eager": {"value": world * args.batch / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager,
                       "note": "same step launched kernel by kernel from Python (no CUDA graph)"},

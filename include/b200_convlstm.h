@@ -50,6 +50,13 @@ int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* src1, int C1,
                              const void* wpacked, const float* bias, int N, int ksize, void* dst,
                              double* stat_sum, double* stat_sumsq, void* stream);
 
+/* nn.ConvTranspose2d(Cin, Cout, 2, stride=2) + F.pad to the skip size (Up, unet.py:90-97) in one kernel: the
+ * GEMM [P, Cin] x [Cin, 4*Cout] (wpacked: bf16 [1][4*Cout (tap, co)][Cin]) whose epilogue adds bias[co] and
+ * writes column block `tap` of input pixel (h, w) to output pixel (2h + tap/2 + oy, 2w + tap%2 + ox) of
+ * y: bf16 [T][B][Hd][Wd][Cout], (oy, ox) = ((Hd-2H)/2, (Wd-2W)/2); y must be zero-filled when Hd > 2H or Wd > 2W. */
+int b200_convT2x2_tc_fwd(const void* x, int Cin, int T, int B, int H, int W, const void* wpacked, const float* bias,
+                         int Cout, void* y, int Hd, int Wd, void* stream);
+
 /* One ConvLSTM cell step, ConvLSTMCell.forward (unet.py:21-36): gate conv over [x ; h_prev] fused
  * with sigmoid/tanh and the c/h update.  wpacked: bf16 [k*k][4*Ch gate-interleaved][Cin+Ch];
  * bias_packed fp32 [4*Ch] in the same row order (b200_pack_lstm_weights).  h_prev / c_prev may be
@@ -166,6 +173,17 @@ int b200_shuffle2x2(const void* src, void* dst, const float* bias, long long IMG
  * boundary: NCHW <-> NHWC; weight packing OIHW <-> [tap][N][K]).  Strides in elements. */
 int b200_strided_copy(const void* src, int src_fp32, void* dst, int dst_fp32, const long long* dims,
                       const long long* src_strides, const long long* dst_strides, int accumulate, void* stream);
+
+/* The reference's training loss `compute_loss` (main.py:28-72): weighted L1 (weight 1 + 4|y|^3) + 0.005 x the
+ * spatial-gradient loss on the [H-1, W-1] crop; with a mask (float 0/1, same shape) the means are masked and
+ * carry the 1e-8 epsilon of main.py:42,65, with mask == NULL they are plain means (main.py:45,67).
+ * y_pred / y / mask / d_y_pred: fp32 [IMG][H][W] (any leading shape flattened to IMG); sums: fp64 [6] workspace
+ * written by the forward pass and read by the backward pass; loss: one fp32 on the device; grad_out: one fp32 on
+ * the device (NULL = 1).  Two passes over the maps instead of ~25 + ~40 element-wise launches. */
+int b200_wl1_grad_loss_fwd(const float* y_pred, const float* y, const float* mask, long long IMG, int H, int W,
+                           double* sums, float* loss, void* stream);
+int b200_wl1_grad_loss_bwd(const float* y_pred, const float* y, const float* mask, long long IMG, int H, int W,
+                           const double* sums, const float* grad_out, float* d_y_pred, void* stream);
 
 #ifdef __cplusplus
 }

@@ -601,3 +601,71 @@ def test_lstm_fused_bptt_matches_stepwise(T, B, H, W, Cin, Ch, have_h0, need_dx,
         if a is not None:
             assert torch.isfinite(f.float()).all(), k
             assert rel2(_np(f), _np(a)) < 6e-3, (k, rel2(_np(f), _np(a)))
+
+
+def test_fused_loss_matches_reference_compute_loss(golden_dir):
+    """unet_convlstm_b200.loss.compute_loss (two fused kernels) against the fixture produced by the reference's
+    own main.compute_loss (tests/golden/make_golden_loss.py): loss and d loss / d y_pred, fp32 arithmetic."""
+    from unet_convlstm_b200.loss import compute_loss
+    z = np.load(os.path.join(golden_dir, "loss_main_compute_loss.npz"))
+    for name in ("a", "b", "c", "z"):
+        for tag in ("mask", "nomask", "ignored"):
+            if f"{name}.{tag}.loss" not in z.files:
+                continue
+            yp = _cuda(z[f"{name}.yp"], True)
+            mask = None if tag == "nomask" else _cuda(z[f"{name}.mask"])
+            loss = compute_loss(yp, _cuda(z[f"{name}.y"]), mask, use_mask=(tag != "ignored"))
+            (3.0 * loss).backward()
+            ref_l, ref_g = float(z[f"{name}.{tag}.loss"]), 3.0 * z[f"{name}.{tag}.grad"]
+            assert abs(float(loss) - ref_l) <= 2e-6 * max(1.0, abs(ref_l)), (name, tag, float(loss), ref_l)
+            np.testing.assert_allclose(_np(yp.grad), ref_g, rtol=2e-5, atol=1e-7 * max(1.0, np.abs(ref_g).max()),
+                                       err_msg=f"{name}.{tag}")
+
+
+def test_fused_loss_fullsize_against_oracle_sample():
+    """BASELINE.json configs[1] size (B = 256, T = 20, 64x64): the loss against the numpy oracle evaluated on the
+    full maps in fp64 (seconds on the CPU) and the gradient on a sample of images."""
+    from oracle import loss_oracle as LO
+    from unet_convlstm_b200.loss import compute_loss
+    g = torch.Generator(device="cuda").manual_seed(2)
+    shape = (256, 20, 1, 64, 64)
+    yp = torch.randn(shape, device="cuda", generator=g).requires_grad_(True)
+    y = torch.randn(shape, device="cuda", generator=g).clamp_(-1, 1)
+    mask = (torch.rand(shape, device="cuda", generator=g) < 0.3).float()
+    loss = compute_loss(yp, y, mask)
+    loss.backward()
+    ref_l, ref_g = LO.compute_loss(_np(yp), _np(y), _np(mask))
+    assert abs(float(loss) - ref_l) <= 1e-5 * abs(ref_l)
+    got = _np(yp.grad)
+    assert rel(got[::37], ref_g[::37]) < 1e-4
+
+
+@pytest.mark.parametrize("T,B,H,W,Cin,Cout,Hd,Wd", [(2, 3, 8, 8, 64, 32, 16, 16), (1, 2, 4, 4, 256, 128, 8, 8),
+                                                    (1, 2, 8, 16, 32, 16, 17, 35),   # F.pad offsets (1 / 3 extra)
+                                                    (2, 4, 32, 32, 128, 64, 64, 64)])
+def test_convT_fused_shuffle_matches_gemm_plus_shuffle(T, B, H, W, Cin, Cout, Hd, Wd):
+    """b200_convT2x2_tc_fwd (pixel shuffle + bias in the GEMM epilogue) against the two-kernel path
+    b200_conv_tc_fwd + b200_shuffle2x2: bit-identical (same accumulation, same single bf16 rounding)."""
+    from unet_convlstm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    bf = torch.bfloat16
+    x = torch.randn(T, B, H, W, Cin, device="cuda", generator=g).to(bf)
+    w = torch.randn(Cin, Cout, 2, 2, device="cuda", generator=g) / Cin ** 0.5
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    wf, _ = ops.pack_convT_weight(w, bf)
+    junk = torch.full((64 << 20,), float("nan"), device="cuda")
+    del junk
+    y = ops.convT2x2_fwd(x, wf, bias, Cout, Hd, Wd)
+    z = torch.empty((T, B, H, W, 4 * Cout), device="cuda", dtype=bf)
+    ops.conv_fwd(x, None, wf, None, 1, z)
+    ref = ops.shuffle2x2(z.float(), bias, Hd, Wd)  # fp32 shuffle of the bf16 GEMM output + bias
+    assert torch.isfinite(y.float()).all()
+    # the fused epilogue adds the bias before the single bf16 rounding, the two-kernel path rounds twice
+    assert rel(_np(y), _np(ref)) < 6e-3
+    # reference ConvTranspose2d arithmetic on the same bf16-rounded operands
+    xt = x.float().permute(0, 1, 4, 2, 3).reshape(T * B, Cin, H, W)
+    rt = torch.nn.functional.conv_transpose2d(xt, w.to(bf).float(), bias, stride=2)
+    oy, ox = (Hd - 2 * H) // 2, (Wd - 2 * W) // 2
+    full = torch.zeros(T * B, Cout, Hd, Wd, device="cuda")
+    full[:, :, oy:oy + 2 * H, ox:ox + 2 * W] = rt
+    assert rel(_np(y.reshape(T * B, Hd, Wd, Cout).permute(0, 3, 1, 2)), _np(full)) < 6e-3

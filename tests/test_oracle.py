@@ -198,3 +198,17 @@ def test_torch_port_convlstm_matches_reference(golden_dir, name):
     assert rel(torch.stack(out).numpy(), z["out"]) < 1e-10
     for l in range(L):
         assert rel(ns[l][1].numpy(), z[f"cT{l}"]) < 1e-10
+
+
+def test_loss_oracle_matches_reference_compute_loss(golden_dir):
+    """oracle/loss_oracle.py against the fixture produced by the reference's own main.compute_loss."""
+    from oracle import loss_oracle as LO
+    z = np.load(os.path.join(golden_dir, "loss_main_compute_loss.npz"))
+    for name in ("a", "b", "c", "z"):
+        for tag in ("mask", "nomask", "ignored"):
+            if f"{name}.{tag}.loss" not in z.files:
+                continue
+            mask = None if tag == "nomask" else z[f"{name}.mask"]
+            loss, grad = LO.compute_loss(z[f"{name}.yp"], z[f"{name}.y"], mask, use_mask=(tag != "ignored"))
+            assert abs(loss - float(z[f"{name}.{tag}.loss"])) <= 1e-12 * max(1.0, abs(loss)), (name, tag)
+            np.testing.assert_allclose(grad, z[f"{name}.{tag}.grad"], rtol=1e-10, atol=1e-14, err_msg=f"{name}.{tag}")

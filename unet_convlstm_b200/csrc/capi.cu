@@ -92,6 +92,22 @@ extern "C" int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* sr
                             /*out_fp32=*/0, /*relu=*/0, /*accumulate=*/0, stat_sum, stat_sumsq, stream);
 }
 
+extern "C" int b200_convT2x2_tc_fwd(const void* x, int Cin, int T, int B, int H, int W, const void* wpacked,
+                                    const float* bias, int Cout, void* y, int Hd, int Wd, void* stream) {
+    if (!x || !wpacked || !y || Cin <= 0 || Cout <= 0 || Cout % 16 != 0 || Hd < 2 * H || Wd < 2 * W) {
+        set_last_error("b200_convT2x2_tc_fwd: bad arguments (Cout must be a multiple of 16, Hd >= 2H, Wd >= 2W)");
+        return B200_ERR_ARG;
+    }
+    ConvTcParams p = {};
+    p.T = T; p.B = B; p.H = H; p.W = W;
+    p.C0 = Cin; p.C1 = 0; p.N = 4 * Cout; p.ksize = 1;
+    p.dst0 = y; p.ld0 = Cout; p.split = 4 * Cout;
+    p.bias = bias;
+    p.shuf_C = Cout; p.shuf_Hd = Hd; p.shuf_Wd = Wd;
+    p.shuf_oy = (Hd - 2 * H) / 2; p.shuf_ox = (Wd - 2 * W) / 2;  // centred like F.pad (unet.py:95-97)
+    return launch_conv_tc(x, nullptr, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch, int B, int H,
                                          int W, const void* wpacked, const float* bias_packed,
                                          const float* c_prev, float* c_next, void* h_next,

@@ -418,12 +418,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
                         if (p.bias) {
+                            const float* bp = p.bias + (p.shuf_C > 0 ? ncol % p.shuf_C : ncol);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ncol + j);
+                            for (int j = 0; j < 16; ++j) f[j] += __ldg(bp + j);
                         }
                         if (p.relu) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (p.shuf_C > 0) {
+                            // ConvTranspose 2x2 stride 2: the tap block of this column chunk selects the output
+                            // pixel of the 2x2 patch (no separate pixel-shuffle pass)
+                            const int tap = ncol / p.shuf_C, co = ncol - tap * p.shuf_C;
+                            const long long img = static_cast<long long>(tc.t) * p.B + tc.b0 + bi;
+                            const long long orow = (img * p.shuf_Hd + 2 * (tc.h0 + hi) + (tap >> 1) + p.shuf_oy) * p.shuf_Wd +
+                                                   2 * (tc.w0 + wi) + (tap & 1) + p.shuf_ox;
+                            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.dst0) + orow * p.shuf_C + co);
+                            o[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                            o[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                              pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                            continue;
                         }
                         const bool second = ncol >= p.split;
                         const long long off = second ? pix * p.ld1 + (ncol - p.split) : pix * p.ld0 + ncol;

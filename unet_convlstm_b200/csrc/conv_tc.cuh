@@ -32,6 +32,10 @@ struct ConvTcParams {
     int relu;
     int accumulate;      // fp32 only: dst += value
     const float* bias;   // [N] (packed order) or nullptr
+    // fused 2x2 pixel shuffle (ConvTranspose2d k=2 s=2 as a GEMM, unet.py:90-97; bf16 output, dst0 only):
+    // column n = tap * shuf_C + co of input pixel (img, h, w) goes to output pixel
+    // (2h + tap/2 + shuf_oy, 2w + tap%2 + shuf_ox) of a [IMG][shuf_Hd][shuf_Wd][shuf_C] tensor; bias is [shuf_C]
+    int shuf_C, shuf_Hd, shuf_Wd, shuf_oy, shuf_ox;
     // fused BatchNorm statistics (bf16 output only): per (t, column) sum and sum of squares of the
     // stored (bf16-rounded) outputs are added to stat_sum / stat_sumsq [T][N] (caller zeroes them)
     double* stat_sum;

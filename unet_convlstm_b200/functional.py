@@ -173,9 +173,7 @@ class ConvT2x2(torch.autograd.Function):
         T, B, H, W, Cin = x.shape
         Cout = weight.shape[1]
         wf, _ = cache.get(("convT", dt), (weight,), lambda: ops.pack_convT_weight(weight, dt))
-        z = torch.empty((T, B, H, W, 4 * Cout), device=x.device, dtype=dt)
-        ops.conv_fwd(x, None, wf, None, 1, z)
-        y = ops.shuffle2x2(z, bias.detach() if bias is not None else None, Hd, Wd)
+        y = ops.convT2x2_fwd(x, wf, bias.detach() if bias is not None else None, Cout, Hd, Wd)
         ctx.save_for_backward(x, weight)
         ctx.cache, ctx.has_bias = cache, bias is not None
         return y

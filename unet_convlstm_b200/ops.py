@@ -327,6 +327,22 @@ def shuffle2x2(z, bias, Hd, Wd):
     return y
 
 
+def convT2x2_fwd(x, wf, bias, Cout, Hd, Wd):
+    """ConvTranspose2d(k=2, s=2) + centring pad: on the tensor-core path one kernel (GEMM + pixel shuffle in the
+    epilogue), otherwise the GEMM followed by b200_shuffle2x2."""
+    _chk(x, "x")
+    T, B, H, W, Cin = x.shape
+    if x.dtype == torch.bfloat16 and Cout % 16 == 0 and tc_conv_ok(x, None, 4 * Cout):
+        exact = (Hd == 2 * H and Wd == 2 * W)
+        y = (torch.empty if exact else torch.zeros)((T, B, Hd, Wd, Cout), device=x.device, dtype=x.dtype)
+        _lib.call("b200_convT2x2_tc_fwd", _p(x), Cin, T, B, H, W, _p(wf), _p(bias), Cout, _p(y), Hd, Wd, _st(),
+                  tag=f"K{Cin} N{4 * Cout} {H}x{W} convT", work=(2.0 * T * B * H * W * Cin * 4 * Cout, None))
+        return y
+    z = torch.empty((T, B, H, W, 4 * Cout), device=x.device, dtype=x.dtype)
+    conv_fwd(x, None, wf, None, 1, z)
+    return shuffle2x2(z, bias, Hd, Wd)
+
+
 def unshuffle2x2(dy, H, W):
     _chk(dy, "dy")
     T, B, Hd, Wd, C = dy.shape
