@@ -50,6 +50,14 @@ int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* src1, int C1,
                              const void* wpacked, const float* bias, int N, int ksize, void* dst,
                              double* stat_sum, double* stat_sumsq, void* stream);
 
+/* Inference form of one half of a DoubleConv stage (Conv3x3 + eval-mode BatchNorm2d + ReLU, unet.py:70-71 with
+ * model.eval()): out = relu(conv(x) * scale[n] + shift[n]), the BatchNorm folded into the GEMM epilogue
+ * (scale = gamma / sqrt(running_var + eps), shift = beta + (conv_bias - running_mean) * scale), so the
+ * pre-activation tensor and the two normalisation passes of the training path do not exist.  dst: bf16. */
+int b200_conv_affine_relu_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H, int W,
+                                 const void* wpacked, const float* scale, const float* shift, int N, int ksize,
+                                 void* dst, int relu, void* stream);
+
 /* nn.ConvTranspose2d(Cin, Cout, 2, stride=2) + F.pad to the skip size (Up, unet.py:90-97) in one kernel: the
  * GEMM [P, Cin] x [Cin, 4*Cout] (wpacked: bf16 [1][4*Cout (tap, co)][Cin]) whose epilogue adds bias[co] and
  * writes column block `tap` of input pixel (h, w) to output pixel (2h + tap/2 + oy, 2w + tap%2 + ox) of

@@ -669,3 +669,41 @@ def test_convT_fused_shuffle_matches_gemm_plus_shuffle(T, B, H, W, Cin, Cout, Hd
     full = torch.zeros(T * B, Cout, Hd, Wd, device="cuda")
     full[:, :, oy:oy + 2 * H, ox:ox + 2 * W] = rt
     assert rel(_np(y.reshape(T * B, Hd, Wd, Cout).permute(0, 3, 1, 2)), _np(full)) < 6e-3
+
+
+def test_inference_folded_batchnorm_matches_eval_path_and_oracle():
+    """model.eval() under torch.no_grad(): DoubleConv runs conv + BatchNorm(eval) + ReLU as ONE kernel
+    (b200_conv_affine_relu_tc_fwd).  Against the unfused eval path of the same model (autograd enabled) and
+    against the fp64 CPU oracle in eval mode with non-trivial running statistics."""
+    import unet_convlstm_b200 as pkg
+    from oracle import torch_port as TP
+    from train.unet import TemporalUNetDualView
+    from unet_convlstm_b200 import _lib
+    pkg.set_precision("bf16")
+    B, T, H, W = 3, 3, 64, 64
+    torch.manual_seed(5)
+    m = TemporalUNetDualView(base_ch=16, use_skip_lstm=True)
+    gen = torch.Generator().manual_seed(6)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data = 0.5 + torch.rand(mod.weight.shape, generator=gen)
+            mod.bias.data = 0.2 * torch.randn(mod.bias.shape, generator=gen)
+            mod.running_mean.data = 0.1 * torch.randn(mod.running_mean.shape, generator=gen)
+            mod.running_var.data = 0.5 + torch.rand(mod.running_var.shape, generator=gen)
+    x = np.random.default_rng(5).random((B, T, 2, H, W)).astype(np.float32)
+    p = TP.params_from_state_dict({k: v.clone() for k, v in m.state_dict().items()}, torch.float64)
+    with torch.no_grad():
+        ref, ref_state = TP.temporal_unet(p, torch.from_numpy(x).double(), None, training=False, track=False)
+    ref = torch.stack(ref, dim=1).numpy()
+    m = m.cuda().eval()
+    xg = torch.from_numpy(x).cuda()
+    out_u, _ = m(xg)                               # autograd enabled: conv, finalize, normalise/ReLU kernels
+    calls0 = dict(_lib.CALLS)
+    with torch.no_grad():
+        out_f, state = m(xg)                       # folded
+    assert _lib.CALLS.get("b200_conv_affine_relu_tc_fwd", 0) - calls0.get("b200_conv_affine_relu_tc_fwd", 0) == 18
+    assert _lib.CALLS.get("b200_bn_relu_apply", 0) == calls0.get("b200_bn_relu_apply", 0)
+    yu, yf = _np(torch.stack(out_u, dim=1)), _np(torch.stack(out_f, dim=1))
+    assert rel2(yf, ref) < 2e-2 and rel2(yu, ref) < 2e-2
+    assert rel2(yf, yu) < 2e-2
+    assert rel2(_np(state[0][0]), ref_state[0][0].numpy()) < 2e-2

@@ -120,6 +120,18 @@ class DoubleConv(nn.Module):
         conv, bn = self.net[3 * i], self.net[3 * i + 1]
         T = x0.shape[0]
         training = self.training or not bn.track_running_stats
+        if not training and not torch.is_grad_enabled() and ops.conv_affine_relu_ok(x0, x1, conv.out_channels):
+            # inference (model.eval() under torch.no_grad()): BatchNorm folded into the conv epilogue -- one kernel
+            # per conv instead of conv + finalize + normalise/ReLU pass
+            K = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
+            wp = self._caches[i].get(("fwd", x0.dtype, K), (conv.weight,),
+                                     lambda: ops.pack_conv_weight(conv.weight, x0.dtype, K))
+            scale, shift = self._caches[i].get(
+                ("bn_eval",), (bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.bias),
+                lambda: ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                                bn.eps, conv.bias))
+            return ops.conv_affine_relu(Fn._c(x0), None if x1 is None else Fn._c(x1), wp, scale, shift,
+                                        conv.kernel_size[0])
         y = Fn.ConvBnRelu.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                 training, bn.eps, bn.momentum if bn.momentum is not None else 0.1, self._caches[i])
         if training and bn.track_running_stats:

@@ -35,7 +35,7 @@ static int conv_tc_fwd_impl(const void* src0, int C0, const void* src1, int C1, 
                            int W, const void* wpacked, const float* bias, int N, int ksize,
                            void* dst0, long long ld0, int split, void* dst1, long long ld1,
                            int out_fp32, int relu, int accumulate, double* stat_sum, double* stat_sumsq,
-                           void* stream) {
+                           const float* scale, void* stream) {
     if (!src0 || !wpacked || !dst0 || T <= 0 || N <= 0 || (ksize & 1) == 0) {
         set_last_error("b200_conv_tc_fwd: bad arguments");
         return B200_ERR_ARG;
@@ -60,13 +60,14 @@ static int conv_tc_fwd_impl(const void* src0, int C0, const void* src1, int C1, 
     if (halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
         conv_halo_supported(T * B, H, W, C0, C1, N, ksize))
         return launch_conv_halo(src0, src1, wpacked, T * B, H, W, C0, C1, N, bias, dst0, ld0, split, dst1, ld1,
-                                out_fp32, relu, accumulate, stat_sum, stat_sumsq, B, static_cast<cudaStream_t>(stream));
+                                out_fp32, relu, accumulate, stat_sum, stat_sumsq, B, scale,
+                                static_cast<cudaStream_t>(stream));
     ConvTcParams p = {};
     p.T = T; p.B = B; p.H = H; p.W = W;
     p.C0 = C0; p.C1 = C1; p.N = N; p.ksize = ksize;
     p.dst0 = dst0; p.dst1 = dst1; p.ld0 = ld0; p.ld1 = ld1; p.split = split;
     p.out_fp32 = out_fp32; p.relu = relu; p.accumulate = accumulate; p.bias = bias;
-    p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
+    p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq; p.scale = scale;
     return launch_conv_tc(src0, src1, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
 }
 
@@ -75,7 +76,7 @@ extern "C" int b200_conv_tc_fwd(const void* src0, int C0, const void* src1, int 
                                 void* dst0, long long ld0, int split, void* dst1, long long ld1,
                                 int out_fp32, int relu, int accumulate, void* stream) {
     return conv_tc_fwd_impl(src0, C0, src1, C1, T, B, H, W, wpacked, bias, N, ksize, dst0, ld0, split, dst1, ld1,
-                            out_fp32, relu, accumulate, nullptr, nullptr, stream);
+                            out_fp32, relu, accumulate, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
@@ -89,7 +90,18 @@ extern "C" int b200_conv_bnstats_tc_fwd(const void* src0, int C0, const void* sr
     B200_CUDA_CHECK(cudaMemsetAsync(stat_sum, 0, sizeof(double) * T * N, st));
     B200_CUDA_CHECK(cudaMemsetAsync(stat_sumsq, 0, sizeof(double) * T * N, st));
     return conv_tc_fwd_impl(src0, C0, src1, C1, T, B, H, W, wpacked, bias, N, ksize, dst, N, N, nullptr, 0,
-                            /*out_fp32=*/0, /*relu=*/0, /*accumulate=*/0, stat_sum, stat_sumsq, stream);
+                            /*out_fp32=*/0, /*relu=*/0, /*accumulate=*/0, stat_sum, stat_sumsq, nullptr, stream);
+}
+
+extern "C" int b200_conv_affine_relu_tc_fwd(const void* src0, int C0, const void* src1, int C1, int T, int B, int H,
+                                           int W, const void* wpacked, const float* scale, const float* shift, int N,
+                                           int ksize, void* dst, int relu, void* stream) {
+    if (!scale || !shift) {
+        set_last_error("b200_conv_affine_relu_tc_fwd: scale and shift are required");
+        return B200_ERR_ARG;
+    }
+    return conv_tc_fwd_impl(src0, C0, src1, C1, T, B, H, W, wpacked, shift, N, ksize, dst, N, N, nullptr, 0,
+                            /*out_fp32=*/0, relu, /*accumulate=*/0, nullptr, nullptr, scale, stream);
 }
 
 extern "C" int b200_convT2x2_tc_fwd(const void* x, int Cin, int T, int B, int H, int W, const void* wpacked,

@@ -45,6 +45,7 @@ struct ConvHaloParams {
     long long ld0, ld1;
     int split, out_fp32, relu, accumulate;
     const float* bias;
+    const float* scale;  // per-channel multiplier applied before the bias (folded eval-mode BatchNorm) or nullptr
     // fused BatchNorm statistics (see ConvTcParams::stat_sum): [IMG / imgs_per_t][N]
     double* stat_sum;
     double* stat_sumsq;
@@ -348,6 +349,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                     float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[g16 * 16 + j]);
+                    if (p.scale) {
+                        const float4* s4 = reinterpret_cast<const float4*>(p.scale + nc);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 ss = __ldg(s4 + j);
+                            f[4 * j] *= ss.x; f[4 * j + 1] *= ss.y; f[4 * j + 2] *= ss.z; f[4 * j + 3] *= ss.w;
+                        }
+                    }
                     if (p.bias) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
 #pragma unroll
@@ -470,7 +479,7 @@ static int launch_halo_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, cons
 int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, int IMG, int H, int W, int C0, int C1,
                      int N, const float* bias, void* dst0, long long ld0, int split, void* dst1, long long ld1,
                      int out_fp32, int relu, int accumulate, double* stat_sum, double* stat_sumsq, int imgs_per_t,
-                     cudaStream_t stream) {
+                     const float* scale, cudaStream_t stream) {
     ConvHaloParams p = {};
     int smem = 0;
     const int block_n = halo_block_n(N);
@@ -479,7 +488,7 @@ int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, in
         return B200_ERR_SHAPE;
     }
     p.dst0 = dst0; p.dst1 = dst1; p.ld0 = ld0; p.ld1 = ld1; p.split = split;
-    p.out_fp32 = out_fp32; p.relu = relu; p.accumulate = accumulate; p.bias = bias;
+    p.out_fp32 = out_fp32; p.relu = relu; p.accumulate = accumulate; p.bias = bias; p.scale = scale;
     p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq; p.imgs_per_t = imgs_per_t > 0 ? imgs_per_t : 1;
     p.err_flag = device_error_flag();
     CUtensorMap ta0, ta1, tb;

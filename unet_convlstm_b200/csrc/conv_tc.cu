@@ -417,6 +417,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.scale) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] *= __ldg(p.scale + ncol + j);
+                        }
                         if (p.bias) {
                             const float* bp = p.bias + (p.shuf_C > 0 ? ncol % p.shuf_C : ncol);
 #pragma unroll

@@ -32,6 +32,7 @@ struct ConvTcParams {
     int relu;
     int accumulate;      // fp32 only: dst += value
     const float* bias;   // [N] (packed order) or nullptr
+    const float* scale;  // [N] or nullptr: out = acc * scale + bias (eval-mode BatchNorm folded into the conv)
     // fused 2x2 pixel shuffle (ConvTranspose2d k=2 s=2 as a GEMM, unet.py:90-97; bf16 output, dst0 only):
     // column n = tap * shuf_C + co of input pixel (img, h, w) goes to output pixel
     // (2h + tap/2 + shuf_oy, 2w + tap%2 + shuf_ox) of a [IMG][shuf_Hd][shuf_Wd][shuf_C] tensor; bias is [shuf_C]
@@ -81,7 +82,7 @@ bool conv_halo_supported(int IMG, int H, int W, int C0, int C1, int N, int ksize
 int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, int IMG, int H, int W, int C0, int C1,
                      int N, const float* bias, void* dst0, long long ld0, int split, void* dst1, long long ld1,
                      int out_fp32, int relu, int accumulate, double* stat_sum, double* stat_sumsq, int imgs_per_t,
-                     cudaStream_t stream);
+                     const float* scale, cudaStream_t stream);
 
 // Picks BLOCK_N for a given GEMM N (multiple of 16).  LSTM epilogue needs N % 64 == 0.
 int pick_block_n(int N, int epi);

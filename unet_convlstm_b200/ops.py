@@ -214,6 +214,37 @@ def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False, bn_ws=None):
     return False
 
 
+def conv_affine_relu_ok(x0, x1, N) -> bool:
+    return x0.dtype == torch.bfloat16 and tc_conv_ok(x0, x1, N)
+
+
+def conv_affine_relu(x0, x1, wp, scale, shift, ksize, relu=True):
+    """Inference: relu(conv_k([x0 ; x1]) * scale + shift) in one kernel (eval-mode BatchNorm folded into the
+    GEMM epilogue, b200_conv_affine_relu_tc_fwd).  Tensor-core path only (see conv_affine_relu_ok)."""
+    _chk(x0, "x0"), _chk(wp, "wp")
+    T, B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else _chk(x1, "x1").shape[-1]
+    N = wp.shape[1]
+    out = torch.empty((T, B, H, W, N), device=x0.device, dtype=x0.dtype)
+    _lib.call("b200_conv_affine_relu_tc_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(scale), _p(shift), N, ksize,
+              _p(out), int(relu), _st(), tag=f"K{C0 + C1} N{N} {H}x{W} k{ksize} +bn(eval)+relu",
+              work=(2.0 * T * B * H * W * ksize * ksize * (C0 + C1) * N, None))
+    return out
+
+
+def bn_eval_scale_shift(gamma, beta, running_mean, running_var, eps, conv_bias):
+    """(scale, shift) of an eval-mode BatchNorm folded behind a conv with bias: y = conv * scale + shift."""
+    C = gamma.numel()
+    dev = gamma.device
+    mean = torch.empty((1, C), device=dev, dtype=torch.float32)
+    rstd, scale, shift = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+    _lib.call("b200_bn_finalize", None, None, 1, 1, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, 0.0, 0,
+              _p(mean), _p(rstd), _p(scale), _p(shift), _st())
+    if conv_bias is not None:
+        shift = torch.addcmul(shift, conv_bias.detach().float().view(1, C), scale)  # [C]-sized parameter algebra
+    return scale.view(C), shift.view(C)
+
+
 def conv_wgrad(dz, src, ksize, dw, koff):
     """dw[tap][n][koff + c] += sum_{t,p} dz[t,p,n] * src[t,p+tap,c]; dw fp32 [k*k, Nz, ldk] (pre-zeroed)."""
     _chk(dz, "dz"), _chk(src, "src"), _chk(dw, "dw")
