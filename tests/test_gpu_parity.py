@@ -370,7 +370,8 @@ def test_conv_fused_bn_stats(T, B, H, W, C0, C1, N):
     out = torch.full((T, B, H, W, N), float("nan"), device="cuda", dtype=torch.bfloat16)
     ws = torch.full((2, T, N), float("nan"), device="cuda", dtype=torch.float64)
     assert ops.conv_fwd(x0, x1, wp, bias, 3, out, bn_ws=ws) is True
-    assert torch.equal(out, plain)
+    # the plain call may run on the CTA-pair kernel (different accumulation order): equal up to bf16 rounding
+    assert rel(_np(out), _np(plain)) < 8e-3
     ref = torch.empty((2, T, N), device="cuda", dtype=torch.float64)
     _lib.call("b200_bn_stats", out.data_ptr(), T, B * H * W, N, 0, ref[0].data_ptr(), ref[1].data_ptr(),
               torch.cuda.current_stream().cuda_stream)

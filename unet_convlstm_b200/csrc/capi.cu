@@ -57,6 +57,23 @@ static int conv_tc_fwd_impl(const void* src0, int C0, const void* src1, int C1, 
         const char* e = getenv("B200_CONV_HALO");
         return e ? atoi(e) : 1;
     }();
+    // CTA-pair kernel (conv_tc2.cu, tcgen05 cta_group::2).  B200_CONV_2CTA: 0 = never, 1 (default) = everywhere
+    // except the N <= 64 layers the halo kernel takes (measured, profiles/r01_conv_2cta_ab.txt: 1.04-1.16x on the
+    // N >= 128 shapes, 0.78x at K64->N64 where loading the activation tile once matters more), 2 = always.
+    static const int pair_mode = [] {
+        const char* e = getenv("B200_CONV_2CTA");
+        return e ? atoi(e) : 1;
+    }();
+    ConvTcParams pp = {};
+    pp.T = T; pp.B = B; pp.H = H; pp.W = W;
+    pp.C0 = C0; pp.C1 = C1; pp.N = N; pp.ksize = ksize;
+    pp.dst0 = dst0; pp.dst1 = dst1; pp.ld0 = ld0; pp.ld1 = ld1; pp.split = split;
+    pp.out_fp32 = out_fp32; pp.relu = relu; pp.accumulate = accumulate; pp.bias = bias;
+    pp.stat_sum = stat_sum; pp.stat_sumsq = stat_sumsq; pp.scale = scale;
+    const bool halo_takes = halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
+                            conv_halo_supported(T * B, H, W, C0, C1, N, ksize);
+    if (pair_mode > 0 && conv_tc2_supported(pp) && (pair_mode >= 2 || !(halo_takes && N <= 64)))
+        return launch_conv_tc2(src0, src1, wpacked, pp, static_cast<cudaStream_t>(stream));
     if (halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
         conv_halo_supported(T * B, H, W, C0, C1, N, ksize))
         return launch_conv_halo(src0, src1, wpacked, T * B, H, W, C0, C1, N, bias, dst0, ld0, split, dst1, ld1,
