@@ -391,8 +391,9 @@ def run_b200_arm(args, out):
                       "note": "same step launched kernel by kernel from Python (no CUDA graph)"},
             "cuda_graph": use_graph,
             "gpu_launches": launches,
-            "roofline": {"kernel": "conv_tc_kernel<256, EPI_LSTM>: fused ConvLSTM gate conv + gate math + c/h update, "
-                                   "forward, one timestep-persistent launch per layer (T steps)",
+            "roofline": {"kernel": "conv_tc2_kernel<256, EPI_LSTM>: fused ConvLSTM gate conv + gate math + c/h update, "
+                                   "forward, CTA pairs (tcgen05 cta_group::2), one timestep-persistent launch per "
+                                   "layer (T steps)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach / peak_tf) if ach else None, "traffic": traffic, "peak_source": peak_src,
                          "launches_timed": len(full),

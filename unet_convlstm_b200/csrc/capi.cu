@@ -73,7 +73,7 @@ static int conv_tc_fwd_impl(const void* src0, int C0, const void* src1, int C1, 
     const bool halo_takes = halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
                             conv_halo_supported(T * B, H, W, C0, C1, N, ksize);
     if (pair_mode > 0 && conv_tc2_supported(pp) && (pair_mode >= 2 || !(halo_takes && N <= 64)))
-        return launch_conv_tc2(src0, src1, wpacked, pp, static_cast<cudaStream_t>(stream));
+        return launch_conv_tc2(src0, src1, wpacked, pp, EPI_STORE, static_cast<cudaStream_t>(stream));
     if (halo_mode > 0 && ksize == 3 && (N <= 128 || halo_mode >= 2) &&
         conv_halo_supported(T * B, H, W, C0, C1, N, ksize))
         return launch_conv_halo(src0, src1, wpacked, T * B, H, W, C0, C1, N, bias, dst0, ld0, split, dst1, ld1,
@@ -179,6 +179,12 @@ extern "C" int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all,
     p.gates_out = static_cast<__nv_bfloat16*>(gates);
     p.seq_T = T;
     p.seq_have_h0 = have_h0;
+    // B200_LSTM_2CTA (default 1): the CTA-pair kernel (conv_tc2.cu, tcgen05 cta_group::2); 0: the 1-CTA kernel
+    static const int pair_mode = [] {
+        const char* e = getenv("B200_LSTM_2CTA");
+        return e ? atoi(e) : 1;
+    }();
+    if (pair_mode > 0) return launch_conv_tc2(x_seq, h_all, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
     return launch_convlstm_seq_tc(x_seq, h_all, wpacked, p, static_cast<cudaStream_t>(stream));
 }
 

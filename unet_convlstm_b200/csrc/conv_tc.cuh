@@ -86,7 +86,7 @@ int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, in
 
 // conv_tc2.cu: the same convolution on a CTA pair (tcgen05 cta_group::2, M = 256 per pair), plain store epilogue.
 bool conv_tc2_supported(const ConvTcParams& p);
-int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, cudaStream_t stream);
+int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi, cudaStream_t stream);
 
 // Picks BLOCK_N for a given GEMM N (multiple of 16).  LSTM epilogue needs N % 64 == 0.
 int pick_block_n(int N, int epi);

@@ -16,6 +16,10 @@
 //             .cta_group::2 with the barrier address mapped to the leader)
 //   empty[s]  one per CTA, signalled in BOTH by the leader's tcgen05.commit.cta_group::2 ... multicast
 //   tfull[a]  one per CTA (multicast commit), tempty[a] in the leader: 4 epilogue warps x 2 CTAs arrive
+// EPI_LSTM (+ the timestep-persistent mode of conv_tc.cu, ConvTcParams::seq_T): the fused ConvLSTM cell.  The
+// gate-interleaved N tile [i f g o] x 64 hidden channels is split [i f] / [g o] between the two CTAs' weight
+// loads; after the 2-CTA MMA each CTA holds all four gates of its own 128 pixels in TMEM, so the cell update is
+// the same lane-local epilogue.  Steps are separated by the grid-wide counter (cooperative cluster launch).
 // Warp roles per CTA as in conv_tc.cu (warp 0 TMA producer, warp 1 MMA issuer -- leader only --, warp 2
 // TMEM allocator, warps 4-7 epilogue); every wait is bounded (watchdog -> trap).
 #include "conv_tc.cuh"
@@ -131,7 +135,21 @@ __device__ __forceinline__ PairTile decode_pair_tile(const ConvTcParams& p, int 
     return tc;
 }
 
-template <int BLOCK_N>
+__device__ __forceinline__ void grid_wait2(const unsigned* ctr, unsigned target, int* err_flag) {
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        if (clock64() - t0 > 8000000000LL) {
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 901;
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    } while (true);
+}
+
+template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                 const __grid_constant__ CUtensorMap tm_b, const ConvTcParams p) {
@@ -158,6 +176,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
     const int chunks0 = p.C0 / p.kc;
     const int chunks = chunks0 + p.C1 / p.kc;
     const int num_kb = taps * chunks;
+    const bool seq = p.seq_T > 0;
+    const int nsteps = seq ? p.seq_T : 1;
     const int num_m_pairs = (p.num_m_tiles + 1) >> 1;
     const int total_ptiles = num_m_pairs * p.num_n_tiles;
     const int num_clusters = gridDim.x >> 1;
@@ -198,14 +218,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
         uint32_t a_dst = smem_base;
         const uint32_t tx_bytes = a_bytes + b_bytes;
         const uint32_t full0_leader = map_to_cta(full_bar(0), 0);  // the leader's full barriers, cluster address
+        for (int step = 0; step < nsteps; ++step) {
+        // zero initial state (unet.py:23-25): the h half of K is skipped at t = 0
+        const int chunks_t = (seq && step == 0 && !p.seq_have_h0) ? chunks0 : chunks;
+        if (seq && step > 0) {
+            // h_{t-1} was written by the epilogue warps of every CTA in the previous step
+            if (lane == 0) grid_wait2(p.sync_ctr, gridDim.x * step, p.err_flag);
+            __syncwarp();
+            fence_proxy_async_all();
+        }
         for (int pt = cluster_id; pt < total_ptiles; pt += num_clusters) {
-            const PairTile tc = decode_pair_tile(p, pt, num_m_pairs, rank, BLOCK_N);
+            PairTile tc = decode_pair_tile(p, pt, num_m_pairs, rank, BLOCK_N);
+            if (seq) tc.t = step;
             const int bn0 = tc.n0 + static_cast<int>(rank) * (BLOCK_N / 2);  // this CTA's half of the weight rows
             int ky = 0, kx = 0;
             for (int tap = 0; tap < taps; ++tap) {
                 const int cw = tc.w0 + kx - p.pad, chh = tc.h0 + ky - p.pad;
                 int kofs = 0;
-                for (int c = 0; c < chunks; ++c, kofs += p.kc) {
+                for (int c = 0; c < chunks_t; ++c, kofs += p.kc) {
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
                     if (elect_one()) {
                         const uint32_t fb = full0_leader + 8u * stage;
@@ -230,6 +260,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                 }
             }
         }
+        }
     } else if (warp == 1) {
         // =================================== MMA issuer (leader CTA only) ===============================
         if (leader) {
@@ -245,12 +276,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
             uint32_t a_lo = (smem_base & 0x3FFFFu) >> 4;
             const uint32_t a_lo0 = a_lo;
             constexpr uint32_t STAGE_LO = Cfg::STAGE_BYTES >> 4, B_LO = Cfg::A_BYTES >> 4;
+            for (int step = 0; step < nsteps; ++step) {
+            const int num_kb_t = (seq && step == 0 && !p.seq_have_h0) ? taps * chunks0 : num_kb;
             for (int pt = cluster_id; pt < total_ptiles; pt += num_clusters) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 uint32_t accum = 0;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = 0; kb < num_kb_t; ++kb) {
                     mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
                     tc_fence_after();
                     if (elect_one()) {
@@ -277,6 +310,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                     acc_phase ^= 1u;
                 }
             }
+            }
         }
     } else if (warp >= 4) {
         // =================================== epilogue (both CTAs, own TMEM lanes) =======================
@@ -288,14 +322,87 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
         const uint32_t tempty0_leader = map_to_cta(tempty_bar(0), 0);
         int acc = 0;
         uint32_t acc_phase = 0;
+        for (int step = 0; step < nsteps; ++step) {
+        const bool zero_state = seq && step == 0 && !p.seq_have_h0;
         for (int pt = cluster_id; pt < total_ptiles; pt += num_clusters) {
-            const PairTile tc = decode_pair_tile(p, pt, num_m_pairs, rank, BLOCK_N);
+            PairTile tc = decode_pair_tile(p, pt, num_m_pairs, rank, BLOCK_N);
+            if (seq) tc.t = step;
             const bool valid = tc.in_range && (tc.h0 + hi < p.H) && (tc.b0 + bi < p.B);
             const long long pix =
                 ((static_cast<long long>(tc.t) * p.B + tc.b0 + bi) * p.H + tc.h0 + hi) * p.W + tc.w0 + wi;
             mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
+            if constexpr (EPI == EPI_LSTM) {
+                // ---- fused LSTM cell update (reference train/unet.py:29-35), as in conv_tc.cu ----
+                constexpr int CHT = BLOCK_N / 4;
+                const int Ch = p.N >> 2;
+                const int ch0 = (tc.n0 >> 2);
+#pragma unroll 1
+                for (int j0 = 0; j0 < CHT; j0 += 16) {
+                    uint32_t vi[16], vf[16], vg[16], vo[16];
+                    tmem_ld16(t_row + 0 * CHT + j0, vi);
+                    tmem_ld16(t_row + 1 * CHT + j0, vf);
+                    tmem_ld16(t_row + 2 * CHT + j0, vg);
+                    tmem_ld16(t_row + 3 * CHT + j0, vo);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    const int ch = ch0 + j0;
+                    // pix already contains the step (tc.t = step); the state slots are indexed by step as well
+                    const long long coff = pix * Ch + ch;
+                    float cp[16];
+                    if (p.c_prev && !zero_state) {
+                        const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + coff);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t4 = c4[j];
+                            cp[4 * j] = t4.x; cp[4 * j + 1] = t4.y; cp[4 * j + 2] = t4.z; cp[4 * j + 3] = t4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+                    }
+                    float gi[16], gf[16], gg[16], go[16], cn[16], hn[16];
+                    const float* bp = p.bias ? p.bias + tc.n0 + j0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float zi = __uint_as_float(vi[j]);
+                        float zf = __uint_as_float(vf[j]);
+                        float zg = __uint_as_float(vg[j]);
+                        float zo = __uint_as_float(vo[j]);
+                        if (bp) {
+                            zi += __ldg(bp + j);
+                            zf += __ldg(bp + CHT + j);
+                            zg += __ldg(bp + 2 * CHT + j);
+                            zo += __ldg(bp + 3 * CHT + j);
+                        }
+                        gi[j] = fast_sigmoid(zi);
+                        gf[j] = fast_sigmoid(zf);
+                        gg[j] = fast_tanh(zg);
+                        go[j] = fast_sigmoid(zo);
+                        cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
+                        hn[j] = go[j] * fast_tanh(cn[j]);
+                    }
+                    auto st16 = [](__nv_bfloat16* dst, const float* sv) {
+                        uint4* o = reinterpret_cast<uint4*>(dst);
+                        o[0] = make_uint4(p_pack_bf16x2(sv[0], sv[1]), p_pack_bf16x2(sv[2], sv[3]),
+                                          p_pack_bf16x2(sv[4], sv[5]), p_pack_bf16x2(sv[6], sv[7]));
+                        o[1] = make_uint4(p_pack_bf16x2(sv[8], sv[9]), p_pack_bf16x2(sv[10], sv[11]),
+                                          p_pack_bf16x2(sv[12], sv[13]), p_pack_bf16x2(sv[14], sv[15]));
+                    };
+                    float4* co = reinterpret_cast<float4*>(p.c_next + coff);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) co[j] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+                    st16(p.h_next + coff, hn);
+                    if (p.gates_out) {
+                        __nv_bfloat16* gb = p.gates_out + pix * (4LL * Ch) + ch;
+                        st16(gb, gi);
+                        st16(gb + Ch, gf);
+                        st16(gb + 2 * Ch, gg);
+                        st16(gb + 3 * Ch, go);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
                 const int ncol = tc.n0 + c16 * 16;
@@ -341,6 +448,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                                       p_pack_bf16x2(f[14], f[15]));
                 }
             }
+            }
             // release the accumulator stage: the MMA issuer (leader) waits for the epilogue warps of BOTH CTAs
             tc_fence_before();
             __syncwarp();
@@ -349,6 +457,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                 acc = 0;
                 acc_phase ^= 1u;
             }
+        }
+        if (seq && step + 1 < nsteps) {
+            // publish h_t / c_t of this CTA's tiles, then signal the grid-wide step counter (see conv_tc.cu)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 4 * 32) {
+                if (step > 0) grid_wait2(p.sync_ctr, gridDim.x * step, p.err_flag);
+                __threadfence();
+                atomicAdd(p.sync_ctr, 1u);
+            }
+        }
         }
     }
 
@@ -363,11 +481,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 static int launch_pair_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb, const ConvTcParams& p,
                             cudaStream_t stream) {
     using Cfg = Tc2Cfg<BLOCK_N>;
-    auto kern = conv_tc2_kernel<BLOCK_N>;
+    auto kern = conv_tc2_kernel<BLOCK_N, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -376,6 +494,23 @@ static int launch_pair_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, cons
     const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int max_clusters = num_sms() / 2;
     const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    if (p.seq_T > 0) {
+        // the steps are separated by a grid-wide counter: every CTA must be resident -> cooperative launch (the
+        // cluster shape comes from the kernel's __cluster_dims__)
+        B200_CUDA_CHECK(cudaMemsetAsync(p.sync_ctr, 0, sizeof(unsigned), stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(P_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta0, ta1, tb, p));
+        return B200_OK;
+    }
     kern<<<2 * clusters, P_THREADS, Cfg::SMEM_BYTES, stream>>>(ta0, ta1, tb, p);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200_OK;
@@ -386,11 +521,19 @@ bool conv_tc2_supported(const ConvTcParams& p) {
     return p.shuf_C == 0 && p.stat_sum == nullptr && p.seq_T == 0 && p.N % 16 == 0;
 }
 
-// Same contract as launch_conv_tc(.., EPI_STORE, ..) for the problems conv_tc2_supported() accepts.
-int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, cudaStream_t stream) {
+// Same contract as launch_conv_tc(.., epi, ..) for EPI_STORE problems conv_tc2_supported() accepts and for
+// EPI_LSTM (single step or timestep-persistent).
+int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, ConvTcParams p, int epi, cudaStream_t stream) {
     if (p.C1 > 0 && !src1) {
         set_last_error("conv_tc2: C1 > 0 but src1 is null");
         return B200_ERR_ARG;
+    }
+    if (p.seq_T > 0) {
+        p.sync_ctr = device_sync_counter();
+        if (!p.sync_ctr) {
+            set_last_error("conv_tc2: no step counter");
+            return B200_ERR_CUDA;
+        }
     }
     const int Ct = p.wK > 0 ? p.wK : p.C0 + p.C1;
     int kc = 64;
@@ -400,7 +543,11 @@ int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, Con
         return B200_ERR_SHAPE;
     }
     p.kc = kc;
-    const int block_n = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
+    const int block_n = epi == EPI_LSTM ? pick_block_n(p.N, EPI_LSTM) : (p.N > 128 ? 256 : (p.N > 64 ? 128 : 64));
+    if (block_n == 0) {
+        set_last_error("conv_tc2: N=%d not supported for the LSTM epilogue", p.N);
+        return B200_ERR_SHAPE;
+    }
     MTile mt;
     if (!plan_mtile(p.B, p.H, p.W, P_BLOCK_M, &mt)) {
         set_last_error("conv_tc2: spatial shape B=%d H=%d W=%d cannot be tiled", p.B, p.H, p.W);
@@ -408,15 +555,17 @@ int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, Con
     }
     p.Wt = mt.Wt; p.Ht = mt.Ht; p.Bt = mt.Bt;
     p.tiles_w = mt.tiles_w; p.tiles_h = mt.tiles_h; p.tiles_b = mt.tiles_b;
+    const int map_T = p.seq_T > 0 ? p.seq_T : p.T;
+    if (p.seq_T > 0) p.T = 1;  // tiles of ONE step; the kernel iterates over the steps itself
     p.num_m_tiles = p.T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
     p.num_n_tiles = (p.N + block_n - 1) / block_n;
     p.pad = p.ksize / 2;
     p.err_flag = device_error_flag();
     CUtensorMap ta0, ta1, tb;
-    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, p.T, kc, mt.Wt, mt.Ht, mt.Bt);
+    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
     if (p.C1 > 0) {
-        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, p.T, kc, mt.Wt, mt.Ht, mt.Bt);
+        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt);
         if (rc != B200_OK) return rc;
     } else {
         ta1 = ta0;
@@ -424,10 +573,17 @@ int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, Con
     // each CTA loads block_n / 2 weight rows; rows beyond N are out-of-bounds reads => zero filled
     rc = make_w_tmap(&tb, wpacked, Ct, p.N, p.ksize * p.ksize, kc, block_n / 2);
     if (rc != B200_OK) return rc;
+    if (epi == EPI_LSTM) {
+        switch (block_n) {
+            case 256: return launch_pair_impl<256, EPI_LSTM>(ta0, ta1, tb, p, stream);
+            case 128: return launch_pair_impl<128, EPI_LSTM>(ta0, ta1, tb, p, stream);
+            default: return launch_pair_impl<64, EPI_LSTM>(ta0, ta1, tb, p, stream);
+        }
+    }
     switch (block_n) {
-        case 256: return launch_pair_impl<256>(ta0, ta1, tb, p, stream);
-        case 128: return launch_pair_impl<128>(ta0, ta1, tb, p, stream);
-        default: return launch_pair_impl<64>(ta0, ta1, tb, p, stream);
+        case 256: return launch_pair_impl<256, EPI_STORE>(ta0, ta1, tb, p, stream);
+        case 128: return launch_pair_impl<128, EPI_STORE>(ta0, ta1, tb, p, stream);
+        default: return launch_pair_impl<64, EPI_STORE>(ta0, ta1, tb, p, stream);
     }
 }
 
