@@ -35,7 +35,7 @@ namespace b200 {
 
 static constexpr int WG_BLOCK_M = 128;
 static constexpr int WG_RB = 64;  // pixels per pipeline stage
-static constexpr int WG_THREADS = 256;
+static constexpr int WG_THREADS = 320;  // warps 0,2,3,8,9 TMA producers, 1 MMA issuer, 4-7 epilogue
 
 struct WgradParams {
     int T, B, H, W;
@@ -168,7 +168,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
-    if (warp == 0 || warp == 2 || warp == 3) {
+    if (warp == 0 || warp == 2 || warp == 3 || warp >= 8) {
         // =================================== TMA producers ==================================
         // The warp runs converged and ONE elected lane (elect.sync) issues every copy of a stage in one
         // straight-line block of UTMALDGs; under a divergent per-lane guard ptxas wraps each copy in an
@@ -176,13 +176,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         // decoded once per unit (registers, the group loop is unrolled), the pixel-block coordinates
         // are carried by nested counters (no divisions in the loop).
         //
-        // THREE producer warps share the issue work (profiles/r01_ncu_wgrad_producer_bound.txt: with one
+        // FIVE producer warps share the issue work (profiles/r01_ncu_wgrad_producer_bound.txt: with one
         // producer the 11 copies per 64-pixel block of the 64-channel layers cost ~2500 cycles of issue
         // against ~1000 cycles of MMA): the tap groups of a block are dealt round-robin, producer 0 also
         // loads the dz boxes.  Every producer walks the same stage sequence (sv, pv), waits for every
         // stage to be free and fills the stages of its own groups.
-        constexpr int NPROD = 3;
-        const int pid = warp == 0 ? 0 : warp - 1;
+        constexpr int NPROD = 5;
+        const int pid = warp == 0 ? 0 : (warp < 8 ? warp - 1 : warp - 5);  // warps 0,2,3,8,9 -> 0..4
         constexpr int MAX_GU = Cfg::MAX_GU;
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0;
@@ -337,7 +337,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             __syncwarp();
             pt ^= 1u;
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // =================================== epilogue =======================================
         const int q = warp - 4;
         const int r = q * 32 + lane;
