@@ -60,12 +60,26 @@ def bench_convbn(K, N, HW, T=20, B=256, ks=3):
     print(f"conv+bnstat K{K} N{N} {HW}x{HW} T{T} B{B}: {ms:8.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
+def bench_convT(Cin, Cout, HW, T=20, B=256):
+    x = torch.randn(T, B, HW, HW, Cin, device=dev).to(bf)
+    w = torch.randn(Cin, Cout, 2, 2, device=dev) / Cin ** 0.5
+    bias = torch.randn(Cout, device=dev)
+    wf, _ = ops.pack_convT_weight(w, bf)
+    fl = 2.0 * T * B * HW * HW * Cin * 4 * Cout
+    by = T * B * HW * HW * (Cin + 4 * Cout) * 2
+    ms = timeit(lambda: ops.convT2x2_fwd(x, wf, bias, Cout, 2 * HW, 2 * HW))
+    print(f"convT Cin{Cin} Cout{Cout} {HW}x{HW} fused={int(ops.CONVT_FUSED)}: {ms:8.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s "
+          f"{by / ms / 1e6:8.1f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
     a = sys.argv[1:]
     if a[0] == "wgrad":
         bench_wgrad(*[int(v) for v in a[1:]])
     elif a[0] == "conv":
         bench_conv(*[int(v) for v in a[1:]])
+    elif a[0] == "convT":
+        bench_convT(*[int(v) for v in a[1:]])
     elif a[0] == "convbn":
         bench_convbn(*[int(v) for v in a[1:]])
     else:

@@ -272,6 +272,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const int half = e >> 2;
         const int r = qw * 32 + lane;
         constexpr int COLS = BLOCK_N / 2;  // columns handled by this warp
+        // 256-bit stores (one transaction per row and 16-channel piece) when every row piece is 32-byte aligned
+        const bool wide = !p.out_fp32 && (p.ld0 % 16 == 0) && (p.dst1 == nullptr || p.ld1 % 16 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.dst0) | reinterpret_cast<uintptr_t>(p.dst1)) & 31) == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         // fused BatchNorm statistics: per-warp partial sums in shared memory (plain read-modify-write by
@@ -383,6 +386,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                             }
                             d4[j] = val;
                         }
+                    } else if (wide) {
+                        st_bf16x16(static_cast<__nv_bfloat16*>(base) + o, f);
                     } else {
                         uint4* d4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + o);
                         d4[0] = make_uint4(h_pack_bf16x2(f[0], f[1]), h_pack_bf16x2(f[2], f[3]),

@@ -437,11 +437,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                             const long long img = static_cast<long long>(tc.t) * p.B + tc.b0 + bi;
                             const long long orow = (img * p.shuf_Hd + 2 * (tc.h0 + hi) + (tap >> 1) + p.shuf_oy) * p.shuf_Wd +
                                                    2 * (tc.w0 + wi) + (tap & 1) + p.shuf_ox;
-                            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.dst0) + orow * p.shuf_C + co);
-                            o[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                            o[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                                              pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                            // shuf_C is a multiple of 16: every piece is 32-byte aligned
+                            st_bf16x16(static_cast<__nv_bfloat16*>(p.dst0) + orow * p.shuf_C + co, f);
                             continue;
                         }
                         const bool second = ncol >= p.split;

@@ -28,7 +28,11 @@
 namespace b200 {
 
 static constexpr int P_BLOCK_M = 128;  // rows per CTA (256 per pair)
-static constexpr int P_THREADS = 256;
+// Epilogue warps per CTA: two warps share each TMEM lane quarter and split the columns of the tile -- the low-K
+// layers (ConvTranspose GEMMs, K = Cin; the 16/64/128-channel 3x3 layers) spend more time draining a tile than
+// accumulating it, and the cell update is latency bound.
+static constexpr int P_EPI_WARPS = 8;
+static constexpr int P_THREADS = (4 + P_EPI_WARPS) * 32;
 
 template <int BLOCK_N>
 struct Tc2Cfg {
@@ -197,7 +201,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);   // multicast commit
-            mbar_init(tempty_bar(s), 8);  // 4 epilogue warps of each CTA (used in the leader only)
+            mbar_init(tempty_bar(s), 2 * P_EPI_WARPS);  // the epilogue warps of both CTAs (used in the leader only)
         }
         fence_mbar_init();
     }
@@ -314,12 +318,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
         }
     } else if (warp >= 4) {
         // =================================== epilogue (both CTAs, own TMEM lanes) =======================
-        const int q = static_cast<int>(threadIdx.x >> 5) - 4;
+        const int ew = static_cast<int>(threadIdx.x >> 5) - 4;
+        const int q = ew & 3;        // TMEM lane quarter == warp % 4
+        const int chalf = ew >> 2;   // which half of the tile's columns this warp drains
+        constexpr int NHALF = P_EPI_WARPS / 4;
         const int r = q * 32 + lane;
         const int wi = r % p.Wt;
         const int hi = (r / p.Wt) % p.Ht;
         const int bi = r / (p.Wt * p.Ht);
         const uint32_t tempty0_leader = map_to_cta(tempty_bar(0), 0);
+        // 256-bit stores need 32-byte aligned rows: row strides that are multiples of 16 bf16 and aligned bases
+        const bool wide = !p.out_fp32 && (p.ld0 % 16 == 0) && (p.dst1 == nullptr || p.ld1 % 16 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.dst0) | reinterpret_cast<uintptr_t>(p.dst1)) & 31) == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int step = 0; step < nsteps; ++step) {
@@ -338,8 +348,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                 constexpr int CHT = BLOCK_N / 4;
                 const int Ch = p.N >> 2;
                 const int ch0 = (tc.n0 >> 2);
+                // 16 hidden channels per iteration: with CHT = 16 (BLOCK_N = 64) only the first warp of a quarter works
+                constexpr int CH_PER = (CHT / NHALF >= 16) ? CHT / NHALF : CHT;
+                const int j_begin = (CHT / NHALF >= 16) ? chalf * CH_PER : (chalf == 0 ? 0 : CHT);
 #pragma unroll 1
-                for (int j0 = 0; j0 < CHT; j0 += 16) {
+                for (int j0 = j_begin; j0 < j_begin + CH_PER && j0 < CHT; j0 += 16) {
                     uint32_t vi[16], vf[16], vg[16], vo[16];
                     tmem_ld16(t_row + 0 * CHT + j0, vi);
                     tmem_ld16(t_row + 1 * CHT + j0, vf);
@@ -383,16 +396,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                         cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
                         hn[j] = go[j] * fast_tanh(cn[j]);
                     }
-                    auto st16 = [](__nv_bfloat16* dst, const float* sv) {
-                        uint4* o = reinterpret_cast<uint4*>(dst);
-                        o[0] = make_uint4(p_pack_bf16x2(sv[0], sv[1]), p_pack_bf16x2(sv[2], sv[3]),
-                                          p_pack_bf16x2(sv[4], sv[5]), p_pack_bf16x2(sv[6], sv[7]));
-                        o[1] = make_uint4(p_pack_bf16x2(sv[8], sv[9]), p_pack_bf16x2(sv[10], sv[11]),
-                                          p_pack_bf16x2(sv[12], sv[13]), p_pack_bf16x2(sv[14], sv[15]));
-                    };
-                    float4* co = reinterpret_cast<float4*>(p.c_next + coff);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) co[j] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+                    // Ch is a multiple of 16 and the state buffers come from the caching allocator (512-byte
+                    // aligned): every 16-channel piece is 32-byte aligned -> 256-bit stores
+                    auto st16 = [](__nv_bfloat16* dst, const float* sv) { st_bf16x16(dst, sv); };
+                    st_f32x8(p.c_next + coff, cn);
+                    st_f32x8(p.c_next + coff + 8, cn + 8);
                     st16(p.h_next + coff, hn);
                     if (p.gates_out) {
                         __nv_bfloat16* gb = p.gates_out + pix * (4LL * Ch) + ch;
@@ -404,7 +412,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                 }
             } else {
 #pragma unroll 1
-            for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
+            for (int c16 = chalf * (BLOCK_N / 16 / NHALF); c16 < (chalf + 1) * (BLOCK_N / 16 / NHALF); ++c16) {
                 const int ncol = tc.n0 + c16 * 16;
                 if (ncol >= p.N) break;  // warp-uniform
                 uint32_t v[16];
@@ -440,6 +448,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                         }
                         o[j] = val;
                     }
+                } else if (wide) {
+                    st_bf16x16(static_cast<__nv_bfloat16*>(base) + off, f);
                 } else {
                     uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off);
                     o[0] = make_uint4(p_pack_bf16x2(f[0], f[1]), p_pack_bf16x2(f[2], f[3]), p_pack_bf16x2(f[4], f[5]),
@@ -460,7 +470,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
         }
         if (seq && step + 1 < nsteps) {
             // publish h_t / c_t of this CTA's tiles, then signal the grid-wide step counter (see conv_tc.cu)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(P_EPI_WARPS * 32) : "memory");
             if (threadIdx.x == 4 * 32) {
                 if (step > 0) grid_wait2(p.sync_ctr, gridDim.x * step, p.err_flag);
                 __threadfence();

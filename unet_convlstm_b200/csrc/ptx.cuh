@@ -222,6 +222,30 @@ __device__ __forceinline__ int stat_col(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// 16 bf16 (32 bytes) of one output row as ONE 256-bit store (STG.256, sm_100): an epilogue thread owns one
+// pixel row, so every store instruction of a warp touches 32 different rows -- one 32-byte transaction per
+// row instead of two 16-byte ones.  `dst` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* dst, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+                 "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// f[0..15] -> 16 bf16 at dst (32-byte aligned)
+__device__ __forceinline__ void st_bf16x16(void* dst, const float* f) {
+    st_global_256(dst, bf16x2_bits(f[0], f[1]), bf16x2_bits(f[2], f[3]), bf16x2_bits(f[4], f[5]), bf16x2_bits(f[6], f[7]),
+                  bf16x2_bits(f[8], f[9]), bf16x2_bits(f[10], f[11]), bf16x2_bits(f[12], f[13]), bf16x2_bits(f[14], f[15]));
+}
+// f[0..7] -> 8 fp32 at dst (32-byte aligned)
+__device__ __forceinline__ void st_f32x8(void* dst, const float* f) {
+    st_global_256(dst, __float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]),
+                  __float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -363,7 +363,7 @@ def convT2x2_fwd(x, wf, bias, Cout, Hd, Wd):
     epilogue), otherwise the GEMM followed by b200_shuffle2x2."""
     _chk(x, "x")
     T, B, H, W, Cin = x.shape
-    if x.dtype == torch.bfloat16 and Cout % 16 == 0 and tc_conv_ok(x, None, 4 * Cout):
+    if CONVT_FUSED and x.dtype == torch.bfloat16 and Cout % 16 == 0 and tc_conv_ok(x, None, 4 * Cout):
         exact = (Hd == 2 * H and Wd == 2 * W)
         y = (torch.empty if exact else torch.zeros)((T, B, Hd, Wd, Cout), device=x.device, dtype=x.dtype)
         _lib.call("b200_convT2x2_tc_fwd", _p(x), Cin, T, B, H, W, _p(wf), _p(bias), Cout, _p(y), Hd, Wd, _st(),
@@ -415,6 +415,9 @@ def lstm_tc_ok(x_t, Ch) -> bool:
     B, H, W, Cin = x_t.shape
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
+
+# ConvTranspose 2x2: pixel shuffle in the GEMM epilogue (1) or GEMM + separate shuffle kernel (0)
+CONVT_FUSED = os.environ.get("B200_CONVT_FUSED", "1") != "0"
 
 # BatchNorm batch statistics in the conv epilogue instead of a separate pass (slower on B200, see functional.py)
 FUSE_BN_STATS = os.environ.get("B200_FUSE_BN_STATS", "0") == "1"
