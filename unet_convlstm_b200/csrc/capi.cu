@@ -12,6 +12,10 @@ using namespace b200;
 namespace b200 {
 int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
                     int ksize, float* dw, long long ldk, int koff, cudaStream_t stream);
+// wgrad_tc2.cu: narrow sources on a CTA pair (tcgen05 cta_group::2)
+bool wgrad_tc2_supported(int Nz, int Csrc, int ksize);
+int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, int ksize, float* dw,
+                     long long ldk, int koff, cudaStream_t stream);
 }
 
 extern "C" int b200_device_error(void) {
@@ -219,6 +223,16 @@ extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, 
         set_last_error("b200_wgrad_tc: bad arguments");
         return B200_ERR_ARG;
     }
+    // B200_WGRAD_2CTA: the CTA-pair kernel (wgrad_tc2.cu) for the narrow-source layers.  0 = never, 1 (default) =
+    // where it measured faster (64-channel source, dz >= 128 channels: 912 -> 1100 TFLOP/s; at Nz = 64 both kernels
+    // sit at the L2 -> SM fill limit of the nine tap-shifted source boxes: 778 vs 762), 2 = wherever it can run.
+    static const int pair_mode = [] {
+        const char* e = getenv("B200_WGRAD_2CTA");
+        return e ? atoi(e) : 1;
+    }();
+    if (pair_mode > 0 && (pair_mode >= 2 || (Csrc == 64 && Nz >= 128)) && (ldk % 4) == 0 && (koff % 4) == 0 &&
+        wgrad_tc2_supported(Nz, Csrc, ksize))
+        return launch_wgrad_tc2(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff, static_cast<cudaStream_t>(stream));
     return launch_wgrad_tc(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff,
                            static_cast<cudaStream_t>(stream));
 }
