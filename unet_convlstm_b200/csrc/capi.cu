@@ -223,14 +223,15 @@ extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, 
         set_last_error("b200_wgrad_tc: bad arguments");
         return B200_ERR_ARG;
     }
-    // B200_WGRAD_2CTA: the CTA-pair kernel (wgrad_tc2.cu) for the narrow-source layers.  0 = never, 1 (default) =
-    // where it measured faster (64-channel source, dz >= 128 channels: 912 -> 1100 TFLOP/s; at Nz = 64 both kernels
-    // sit at the L2 -> SM fill limit of the nine tap-shifted source boxes: 778 vs 762), 2 = wherever it can run.
+    // B200_WGRAD_2CTA: the CTA-pair kernel (wgrad_tc2.cu).  0 = never, 1 (default) = where it measured faster or
+    // equal (profiles/r01_wgrad_2cta_ab.txt): every wide-source shape it supports (1.00-1.19x) and 64-channel sources
+    // with dz >= 128 channels (912 -> 1100 TFLOP/s; at Nz = 64 both kernels sit at the L2 -> SM fill limit of the
+    // nine tap-shifted source boxes: 778 vs 762), 2 = wherever it can run.
     static const int pair_mode = [] {
         const char* e = getenv("B200_WGRAD_2CTA");
         return e ? atoi(e) : 1;
     }();
-    if (pair_mode > 0 && (pair_mode >= 2 || (Csrc == 64 && Nz >= 128)) && (ldk % 4) == 0 && (koff % 4) == 0 &&
+    if (pair_mode > 0 && (pair_mode >= 2 || Csrc > 64 || (Csrc == 64 && Nz >= 128)) && (ldk % 4) == 0 && (koff % 4) == 0 &&
         wgrad_tc2_supported(Nz, Csrc, ksize))
         return launch_wgrad_tc2(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff, static_cast<cudaStream_t>(stream));
     return launch_wgrad_tc(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff,

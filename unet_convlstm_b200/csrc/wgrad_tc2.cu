@@ -1,5 +1,10 @@
-// Weight-gradient GEMM of the NARROW layers (source with 16 / 32 / 64 channels) on a CTA PAIR
-// (tcgen05 cta_group::2): the 2-SM variant of wgrad_tc.cu's stacked mode.
+// Weight-gradient GEMM on a CTA PAIR (tcgen05 cta_group::2): the 2-SM variants of wgrad_tc.cu.
+//
+// NORMAL mode (wide sources): A = dz, the pair covers 256 dz channels (CTA r its own 128), B = source channels,
+// each CTA loads HALF of the source tile of every tap -- the varying operand, nine tap-shifted copies of it per
+// pixel block, is what the 1-CTA kernel spends its L2 -> SM bandwidth on.
+//
+// STACKED mode (source with 16 / 32 / 64 channels):
 //
 //   dW[tap][n][koff + c] (+)= sum_{t, pixel p} dz[t, p, n] * src[t, p + tap, c]
 //
@@ -29,24 +34,27 @@ struct Wgrad2Params {
     int T, B, H, W;
     int Nz, Csrc;
     int ksize, pad, taps;
-    int cwS;                    // channel width of one dz box (BLOCK_N / 2 capped at 64)
+    int cwS;                    // channel width of one dz box
+    int cwV;                    // channel width of one source box
     int Wt, Ht, Bt, tiles_w, tiles_h, tiles_b;
     int num_rblocks, rb_per_split, splits;
     int G;                      // taps per CTA and group (128 / Csrc); a pair group has 2G taps
     int ngroups, GU, ngsets;
-    int s_tiles, out_tiles;
+    int s_tiles, v_tiles, out_tiles;
     float* dw;
     long long ldk;
     int koff;
     int* err_flag;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STACKED>
 struct Wg2Cfg {
-    static constexpr int V_BYTES = W2_BLOCK_M * W2_RB * 2;      // this CTA's G stacked tap boxes: 16 KB
-    static constexpr int S_BYTES = (BLOCK_N / 2) * W2_RB * 2;   // this CTA's half of the dz tile
-    static constexpr int SV = (BLOCK_N == 256) ? 4 : 5;
-    static constexpr int SS = (BLOCK_N == 256) ? 2 : 3;
+    static constexpr int A_BYTES = W2_BLOCK_M * W2_RB * 2;     // this CTA's 128 M rows: 32 KB
+    static constexpr int B_BYTES = (BLOCK_N / 2) * W2_RB * 2;  // this CTA's half of the N operand
+    static constexpr int V_BYTES = STACKED ? A_BYTES : B_BYTES;  // varying (source) operand
+    static constexpr int S_BYTES = STACKED ? B_BYTES : A_BYTES;  // shared (dz) operand
+    static constexpr int SV = STACKED ? ((BLOCK_N == 256) ? 4 : 5) : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
+    static constexpr int SS = STACKED ? ((BLOCK_N == 256) ? 2 : 3) : ((BLOCK_N == 256) ? 2 : 3);
     static constexpr int MAX_GU = 512 / BLOCK_N;
     static constexpr int SMEM_BYTES = SV * V_BYTES + SS * S_BYTES + 1024 + 512;
 };
@@ -54,28 +62,34 @@ struct Wg2Cfg {
 __device__ __forceinline__ void w2_red_add_f32(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
+__device__ __forceinline__ void w2_red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 struct Wg2Unit {
-    int split, gset, s0, ngr;
+    int split, gset, s0, v0, ngr;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STACKED>
 __device__ __forceinline__ Wg2Unit wg2_decode(const Wgrad2Params& p, int unit) {
     Wg2Unit u;
     u.split = unit / p.out_tiles;
-    const int ot = unit - u.split * p.out_tiles;
+    int ot = unit - u.split * p.out_tiles;
+    const int vt = ot % p.v_tiles;
+    ot /= p.v_tiles;
     const int st = ot % p.s_tiles;
     u.gset = ot / p.s_tiles;
-    u.s0 = st * BLOCK_N;
+    u.s0 = st * (STACKED ? BLOCK_N : 2 * W2_BLOCK_M);  // stacked: dz channels are N; normal: 256 dz rows per pair
+    u.v0 = vt * BLOCK_N;
     u.ngr = min(p.GU, p.ngroups - u.gset * p.GU);
     return u;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STACKED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, 1)
 wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_src,
                  const Wgrad2Params p) {
-    using Cfg = Wg2Cfg<BLOCK_N>;
+    using Cfg = Wg2Cfg<BLOCK_N, STACKED>;
     constexpr int SV = Cfg::SV, SS = Cfg::SS;
 
     extern __shared__ uint8_t smem_raw[];
@@ -100,11 +114,15 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
     const int num_clusters = gridDim.x >> 1;
     const int cluster_id = blockIdx.x >> 1;
     const int total_units = p.out_tiles * p.splits;
-    const int cwA = p.Csrc;   // A operand: stacked source boxes, one box per tap
-    const int cwB = p.cwS;    // B operand: dz boxes
+    // A operand (this CTA's 128 M rows): stacked -> G source boxes (one per tap), normal -> dz boxes
+    const int cwA = STACKED ? p.cwV : p.cwS;
+    const int cwB = STACKED ? p.cwS : p.cwV;
     const uint32_t boxA_bytes = W2_RB * cwA * 2;
     const uint32_t boxB_bytes = W2_RB * cwB * 2;
-    const int boxesS = (BLOCK_N / 2) / cwB;  // dz boxes per CTA and pixel block
+    const uint32_t boxS_bytes = STACKED ? boxB_bytes : boxA_bytes;
+    const uint32_t boxV_bytes = STACKED ? boxA_bytes : boxB_bytes;
+    const int boxesS = (STACKED ? BLOCK_N / 2 : W2_BLOCK_M) / p.cwS;  // dz boxes per CTA and pixel block
+    const int boxesV = STACKED ? p.G : (BLOCK_N / 2) / p.cwV;         // source boxes per CTA and group
     int tmem_cols = 32;
     while (tmem_cols < p.GU * BLOCK_N) tmem_cols <<= 1;
 
@@ -144,19 +162,22 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0;
         for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
-            const Wg2Unit u = wg2_decode<BLOCK_N>(p, unit);
+            const Wg2Unit u = wg2_decode<BLOCK_N, STACKED>(p, unit);
             const int rb_begin = u.split * p.rb_per_split;
             const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
             // first tap (kx, ky) of this CTA's part of every group of this unit
             int gkx[MAX_GU], gky[MAX_GU];
 #pragma unroll
             for (int g = 0; g < MAX_GU; ++g) {
-                const int tp = min(((u.gset * p.GU + g) * 2 + static_cast<int>(rank)) * p.G, p.taps - 1);
+                const int tp = STACKED ? min(((u.gset * p.GU + g) * 2 + static_cast<int>(rank)) * p.G, p.taps - 1)
+                                       : min(u.gset * p.GU + g, p.taps - 1);
                 gky[g] = tp / p.ksize;
                 gkx[g] = tp - gky[g] * p.ksize;
             }
-            const uint32_t s_tx = boxesS * boxB_bytes, v_tx = p.G * boxA_bytes;
-            const int sc0 = u.s0 + static_cast<int>(rank) * (BLOCK_N / 2);  // this CTA's half of the dz tile
+            const uint32_t s_tx = boxesS * boxS_bytes, v_tx = boxesV * boxV_bytes;
+            // this CTA's dz channels: stacked -> its half of the N tile, normal -> its 128 of the pair's 256 M rows
+            const int sc0 = u.s0 + static_cast<int>(rank) * (STACKED ? BLOCK_N / 2 : W2_BLOCK_M);
+            const int vc0 = u.v0 + static_cast<int>(rank) * (BLOCK_N / 2);  // normal: its half of the source tile
             int m = rb_begin;
             int wt = m % p.tiles_w;
             m /= p.tiles_w;
@@ -173,7 +194,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
                         mbar_arrive_expect_tx_cluster(fb, s_tx);
                         uint32_t dst = s_base + ss * Cfg::S_BYTES;
                         int sc = sc0;
-                        for (int i = 0; i < boxesS; ++i, dst += boxB_bytes, sc += cwB)
+                        for (int i = 0; i < boxesS; ++i, dst += boxS_bytes, sc += p.cwS)
                             tma2_load_5d(dst, &tm_dz, fb, sc, w0, h0, b0, t);
                     }
                     __syncwarp();
@@ -192,16 +213,23 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
                                 const uint32_t fb = vfull0_l + 8u * sv;
                                 mbar_arrive_expect_tx_cluster(fb, v_tx);
                                 uint32_t dst = v_base + sv * Cfg::V_BYTES;
-                                // G consecutive taps; taps beyond the filter repeat the last one (never stored)
-                                int kx = gkx[g], ky = gky[g];
-                                for (int i = 0; i < p.G; ++i, dst += boxA_bytes) {
-                                    tma2_load_5d(dst, &tm_src, fb, 0, w0 + kx - p.pad, h0 + ky - p.pad, b0, t);
-                                    if (ky * p.ksize + kx + 1 < p.taps) {
-                                        if (++kx == p.ksize) {
-                                            kx = 0;
-                                            ++ky;
+                                if (STACKED) {
+                                    // G consecutive taps; taps beyond the filter repeat the last one (never stored)
+                                    int kx = gkx[g], ky = gky[g];
+                                    for (int i = 0; i < boxesV; ++i, dst += boxV_bytes) {
+                                        tma2_load_5d(dst, &tm_src, fb, 0, w0 + kx - p.pad, h0 + ky - p.pad, b0, t);
+                                        if (ky * p.ksize + kx + 1 < p.taps) {
+                                            if (++kx == p.ksize) {
+                                                kx = 0;
+                                                ++ky;
+                                            }
                                         }
                                     }
+                                } else {
+                                    const int cw = w0 + gkx[g] - p.pad, chh = h0 + gky[g] - p.pad;
+                                    int c = vc0;
+                                    for (int i = 0; i < boxesV; ++i, dst += boxV_bytes, c += p.cwV)
+                                        tma2_load_5d(dst, &tm_src, fb, c, cw, chh, b0, t);
                                 }
                             }
                             __syncwarp();
@@ -237,7 +265,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
             int sv = 0, ss = 0;
             uint32_t pv = 0, ps = 0, pt = 0;
             for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
-                const Wg2Unit u = wg2_decode<BLOCK_N>(p, unit);
+                const Wg2Unit u = wg2_decode<BLOCK_N, STACKED>(p, unit);
                 const int rb_begin = u.split * p.rb_per_split;
                 const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
                 mbar_wait(tempty, pt ^ 1u, p.err_flag, 700);
@@ -251,8 +279,9 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
                         mbar_wait(vfull(sv), pv, p.err_flag, 620 + sv);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t adesc = hiA | (v_lo0 + sv * (Cfg::V_BYTES >> 4));
-                            const uint64_t bdesc = hiB | s_lo;
+                            const uint32_t v_lo = v_lo0 + sv * (Cfg::V_BYTES >> 4);
+                            const uint64_t adesc = hiA | (STACKED ? v_lo : s_lo);
+                            const uint64_t bdesc = hiB | (STACKED ? s_lo : v_lo);
                             umma2_bf16(d_tmem, adesc, bdesc, idesc, accum);
 #pragma unroll
                             for (int k = 1; k < W2_RB / 16; ++k)
@@ -285,18 +314,27 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
         const uint32_t tempty_l = map_to_cta(tempty, 0);
         uint32_t pt = 0;
         for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
-            const Wg2Unit u = wg2_decode<BLOCK_N>(p, unit);
-            const int ncols = min(BLOCK_N, p.Nz - u.s0);
+            const Wg2Unit u = wg2_decode<BLOCK_N, STACKED>(p, unit);
+            const int ncols = STACKED ? min(BLOCK_N, p.Nz - u.s0) : min(BLOCK_N, p.Csrc - u.v0);
             mbar_wait(tfull, pt, p.err_flag, 800);
             pt ^= 1u;
             tc_fence_after();
             for (int g = 0; g < u.ngr; ++g) {
                 const int grp = u.gset * p.GU + g;
-                // row r of this CTA = (tap within its G taps, source channel); column = dz channel
-                const int gi = r / p.Csrc, c = r - gi * p.Csrc;
-                const int tp = (grp * 2 + static_cast<int>(rank)) * p.G + gi;
-                const bool valid = tp < p.taps;
-                float* row = p.dw + (static_cast<long long>(valid ? tp : 0) * p.Nz + u.s0) * p.ldk + p.koff + c;
+                bool valid;
+                float* row;
+                if (STACKED) {
+                    // row r of this CTA = (tap within its G taps, source channel); column = dz channel
+                    const int gi = r / p.Csrc, c = r - gi * p.Csrc;
+                    const int tp = (grp * 2 + static_cast<int>(rank)) * p.G + gi;
+                    valid = tp < p.taps;
+                    row = p.dw + (static_cast<long long>(valid ? tp : 0) * p.Nz + u.s0) * p.ldk + p.koff + c;
+                } else {
+                    // row r of this CTA = dz channel; column = source channel
+                    const int n = u.s0 + static_cast<int>(rank) * W2_BLOCK_M + r;
+                    valid = n < p.Nz;
+                    row = p.dw + (static_cast<long long>(grp) * p.Nz + (valid ? n : 0)) * p.ldk + p.koff + u.v0;
+                }
                 const uint32_t t_row = tmem_base + g * BLOCK_N + (uint32_t(q * 32) << 16);
 #pragma unroll 1
                 for (int c16 = 0; c16 * 16 < ncols; ++c16) {
@@ -304,14 +342,30 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
                     tmem_ld16(t_row + c16 * 16, v);
                     tmem_ld_wait();
                     if (!valid) continue;
-                    // transposed store: consecutive lanes hold consecutive source channels
-                    float* o = row + static_cast<long long>(c16) * 16 * p.ldk;
+                    if (STACKED) {
+                        // transposed store: consecutive lanes hold consecutive source channels
+                        float* o = row + static_cast<long long>(c16) * 16 * p.ldk;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (p.splits > 1)
-                            w2_red_add_f32(o + j * p.ldk, __uint_as_float(v[j]));
-                        else
-                            o[j * p.ldk] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; ++j) {
+                            if (p.splits > 1)
+                                w2_red_add_f32(o + j * p.ldk, __uint_as_float(v[j]));
+                            else
+                                o[j * p.ldk] = __uint_as_float(v[j]);
+                        }
+                    } else {
+                        float* o = row + c16 * 16;
+                        if (p.splits > 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                w2_red_add_v4(o + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<float4*>(o)[j] =
+                                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
                     }
                 }
             }
@@ -330,10 +384,10 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
     }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STACKED>
 static int launch_wgrad2_impl(const CUtensorMap& tz, const CUtensorMap& ts, const Wgrad2Params& p, cudaStream_t stream) {
-    using Cfg = Wg2Cfg<BLOCK_N>;
-    auto kern = wgrad_tc2_kernel<BLOCK_N>;
+    using Cfg = Wg2Cfg<BLOCK_N, STACKED>;
+    auto kern = wgrad_tc2_kernel<BLOCK_N, STACKED>;
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -347,12 +401,18 @@ static int launch_wgrad2_impl(const CUtensorMap& tz, const CUtensorMap& ts, cons
     return B200_OK;
 }
 
-// The pair kernel takes the narrow sources (the stacked mode of wgrad_tc.cu) with 3x3 filters and a dz width that
-// is a multiple of its N tile.
+static bool w2_stacked(int Csrc, int ksize) { return (Csrc == 16 || Csrc == 32 || Csrc == 64) && ksize * ksize > 1; }
+
+// Stacked mode: narrow sources, dz width a multiple of its N tile.  Normal mode: dz channels in pairs of 128 and a
+// source width that is a multiple of its N tile (the ConvLSTM weight gradients and the deep UNet layers).
 bool wgrad_tc2_supported(int Nz, int Csrc, int ksize) {
-    if (!(Csrc == 16 || Csrc == 32 || Csrc == 64) || ksize * ksize <= 1) return false;
-    const int block_n = Nz > 128 ? 256 : (Nz > 64 ? 128 : 64);
-    return Nz % block_n == 0;
+    if (w2_stacked(Csrc, ksize)) {
+        const int block_n = Nz > 128 ? 256 : (Nz > 64 ? 128 : 64);
+        return Nz % block_n == 0;
+    }
+    if (Csrc < 64 || Nz % (2 * W2_BLOCK_M) != 0) return false;
+    const int block_n = Csrc > 128 ? 256 : (Csrc > 64 ? 128 : 64);
+    return Csrc % block_n == 0;
 }
 
 int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, int ksize, float* dw,
@@ -360,27 +420,41 @@ int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, i
     Wgrad2Params p = {};
     p.T = T; p.B = B; p.H = H; p.W = W;
     p.Nz = Nz; p.Csrc = Csrc; p.ksize = ksize; p.pad = ksize / 2; p.taps = ksize * ksize;
-    const int block_n = Nz > 128 ? 256 : (Nz > 64 ? 128 : 64);
-    p.cwS = (block_n / 2) < 64 ? (block_n / 2) : 64;
+    const bool stacked = w2_stacked(Csrc, ksize);
+    int block_n;
     MTile mt;
     if (!plan_mtile(B, H, W, W2_RB, &mt)) {
         set_last_error("wgrad_tc2: spatial shape B=%d H=%d W=%d cannot be tiled", B, H, W);
         return B200_ERR_SHAPE;
     }
+    if (stacked) {
+        block_n = Nz > 128 ? 256 : (Nz > 64 ? 128 : 64);
+        p.cwS = (block_n / 2) < 64 ? (block_n / 2) : 64;
+        p.cwV = Csrc;
+        p.G = W2_BLOCK_M / Csrc;
+        p.s_tiles = Nz / block_n;
+        p.v_tiles = 1;
+        p.ngroups = (p.taps + 2 * p.G - 1) / (2 * p.G);
+    } else {
+        block_n = Csrc > 128 ? 256 : (Csrc > 64 ? 128 : 64);
+        p.cwS = 64;
+        p.cwV = (block_n / 2) < 64 ? (block_n / 2) : 64;
+        p.G = 1;
+        p.s_tiles = Nz / (2 * W2_BLOCK_M);
+        p.v_tiles = Csrc / block_n;
+        p.ngroups = p.taps;
+    }
     p.Wt = mt.Wt; p.Ht = mt.Ht; p.Bt = mt.Bt;
     p.tiles_w = mt.tiles_w; p.tiles_h = mt.tiles_h; p.tiles_b = mt.tiles_b;
     p.num_rblocks = T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
-    p.G = W2_BLOCK_M / Csrc;
-    p.s_tiles = Nz / block_n;
-    p.ngroups = (p.taps + 2 * p.G - 1) / (2 * p.G);
     p.GU = 512 / block_n;
     if (p.GU > p.ngroups) p.GU = p.ngroups;
     p.ngsets = (p.ngroups + p.GU - 1) / p.GU;
     p.GU = (p.ngroups + p.ngsets - 1) / p.ngsets;
-    p.out_tiles = p.ngsets * p.s_tiles;
-    // reduction split over the clusters (see wgrad_tc.cu): fewest waves per split, at least 8 blocks per unit
+    p.out_tiles = p.ngsets * p.s_tiles * p.v_tiles;
+    // reduction split over the clusters (see wgrad_tc.cu): fewest waves per split, at least 4 blocks per unit
     const int ncl = num_sms() / 2;
-    int max_splits = (p.num_rblocks + 7) / 8;
+    int max_splits = (p.num_rblocks + 3) / 4;
     if (max_splits > 4 * ncl) max_splits = 4 * ncl;
     if (max_splits < 1) max_splits = 1;
     int best = 1;
@@ -401,12 +475,19 @@ int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, i
     CUtensorMap tz, ts;
     int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.cwS, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
-    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, Csrc, mt.Wt, mt.Ht, mt.Bt);
+    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.cwV, mt.Wt, mt.Ht, mt.Bt);
     if (rc != B200_OK) return rc;
+    if (stacked) {
+        switch (block_n) {
+            case 256: return launch_wgrad2_impl<256, true>(tz, ts, p, stream);
+            case 128: return launch_wgrad2_impl<128, true>(tz, ts, p, stream);
+            default: return launch_wgrad2_impl<64, true>(tz, ts, p, stream);
+        }
+    }
     switch (block_n) {
-        case 256: return launch_wgrad2_impl<256>(tz, ts, p, stream);
-        case 128: return launch_wgrad2_impl<128>(tz, ts, p, stream);
-        default: return launch_wgrad2_impl<64>(tz, ts, p, stream);
+        case 256: return launch_wgrad2_impl<256, false>(tz, ts, p, stream);
+        case 128: return launch_wgrad2_impl<128, false>(tz, ts, p, stream);
+        default: return launch_wgrad2_impl<64, false>(tz, ts, p, stream);
     }
 }
 
