@@ -84,8 +84,18 @@ class ConvBnRelu(torch.autograd.Function):
         ks = weight.shape[2]
         if K > C0 + C1 or (x1 is not None and K != C0 + C1):
             raise ValueError(f"conv weight expects {K} input channels, got {C0}+{C1}")
-        wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
         z = torch.empty((T, B, H, W, N), device=x0.device, dtype=dt)
+        first = ops.FIRST_LAYER_DIRECT and ops.conv_first_ok(x0, x1, weight)
+        if first:
+            # the UNet's first conv (K = 2*9): HBM-bound, CUDA-core kernel on the un-padded weights
+            ops.conv_first_fwd(x0, weight, bias.detach() if bias is not None else None, z)
+            y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum)
+            ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
+            ctx.tstride = stats[4]
+            ctx.training, ctx.cache, ctx.has_bias, ctx.first = training, cache, bias is not None, True
+            return y
+        ctx.first = False
+        wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
         # The BatchNorm sums CAN come out of the conv epilogue (b200_conv_bnstats_tc_fwd), but measured on
         # B200 the cross-lane column reduction makes the epilogue of the narrow layers longer than their
         # main loop (K64->N64 @64x64: +1.05 ms per call against 0.65 ms for the separate HBM-bound
@@ -114,11 +124,14 @@ class ConvBnRelu(torch.autograd.Function):
         dz, dgamma, dbeta, dbias = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
                                                    ctx.has_bias)
         # weight gradient, batched over all T*B images
-        dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
-        ops.conv_wgrad(dz, x0, ks, dwp, 0)
-        if x1 is not None:
-            ops.conv_wgrad(dz, x1, ks, dwp, C0)
-        dweight = ops.unpack_conv_wgrad(dwp, K)
+        if ctx.first:
+            dweight = ops.conv_first_wgrad(dz, x0, K)
+        else:
+            dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
+            ops.conv_wgrad(dz, x0, ks, dwp, 0)
+            if x1 is not None:
+                ops.conv_wgrad(dz, x1, ks, dwp, C0)
+            dweight = ops.unpack_conv_wgrad(dwp, K)
         # data gradient, split over the two sources of the virtual concat
         dx0 = dx1 = None
         need0, need1 = ctx.needs_input_grad[0], (x1 is not None and ctx.needs_input_grad[1])

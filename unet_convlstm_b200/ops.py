@@ -214,6 +214,32 @@ def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False, bn_ws=None):
     return False
 
 
+def conv_first_ok(x0, x1, weight) -> bool:
+    """The UNet's first convolution (2 input channels zero-padded to one K chunk): CUDA-core kernels."""
+    return (x1 is None and x0.dtype == torch.bfloat16 and weight.shape[2] == 3 and weight.shape[3] == 3
+            and weight.shape[1] < 16 and weight.shape[0] % 64 == 0
+            and _lib.supported("b200_conv_first_supported", weight.shape[1], weight.shape[0]))
+
+
+def conv_first_fwd(x0, weight, bias, out):
+    _chk(x0, "x0"), _chk(out, "out")
+    T, B, H, W, Cx = x0.shape
+    N, cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().float().contiguous()
+    _lib.call("b200_conv_first_fwd", _p(x0), Cx, cin, _p(w), _p(bias), _p(out), T * B, H, W, N, _st(),
+              tag=f"cin{cin} N{N} {H}x{W} first", work=(None, (x0.numel() + out.numel()) * 2))
+    return out
+
+
+def conv_first_wgrad(dz, x0, cin):
+    _chk(dz, "dz"), _chk(x0, "x0")
+    T, B, H, W, N = dz.shape
+    dw = torch.empty((N, cin, 3, 3), device=dz.device, dtype=torch.float32)
+    _lib.call("b200_conv_first_wgrad", _p(dz), N, _p(x0), x0.shape[-1], cin, T * B, H, W, _p(dw), _st(),
+              tag=f"cin{cin} N{N} {H}x{W} first", work=(None, (x0.numel() + dz.numel()) * 2))
+    return dw
+
+
 def conv_affine_relu_ok(x0, x1, N) -> bool:
     return x0.dtype == torch.bfloat16 and tc_conv_ok(x0, x1, N)
 
@@ -415,6 +441,11 @@ def lstm_tc_ok(x_t, Ch) -> bool:
     B, H, W, Cin = x_t.shape
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
+
+# First UNet convolution (2 input channels): zero-padded to 16 channels on the tensor-core path (0, default) or the
+# CUDA-core kernels of first_layer.cu (1).  Measured in the cfg-2 step: tensor-core 3.8 ms fwd + 2.4 ms wgrad, the
+# straightforward CUDA-core kernels 8.1 + 15.6 ms -- kept opt-in with their parity test, not used.
+FIRST_LAYER_DIRECT = os.environ.get("B200_FIRST_LAYER_DIRECT", "0") == "1"
 
 # ConvTranspose 2x2: pixel shuffle in the GEMM epilogue (1) or GEMM + separate shuffle kernel (0)
 CONVT_FUSED = os.environ.get("B200_CONVT_FUSED", "1") != "0"
