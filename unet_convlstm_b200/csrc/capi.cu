@@ -138,6 +138,13 @@ extern "C" int b200_convT2x2_tc_fwd(const void* x, int Cin, int T, int B, int H,
     p.bias = bias;
     p.shuf_C = Cout; p.shuf_Hd = Hd; p.shuf_Wd = Wd;
     p.shuf_oy = (Hd - 2 * H) / 2; p.shuf_ox = (Wd - 2 * W) / 2;  // centred like F.pad (unet.py:95-97)
+    // CTA-pair kernel by default (low-K GEMM: 8 epilogue warps per CTA drain the tile); B200_CONV_2CTA=0 -> 1 CTA
+    static const int pair_mode = [] {
+        const char* e = getenv("B200_CONV_2CTA");
+        return e ? atoi(e) : 1;
+    }();
+    if (pair_mode > 0 && conv_tc2_supported(p))
+        return launch_conv_tc2(x, nullptr, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
     return launch_conv_tc(x, nullptr, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
 }
 

@@ -362,12 +362,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                     for (int j = 0; j < 16; ++j) f[j] *= __ldg(p.scale + ncol + j);
                 }
                 if (p.bias) {
+                    const float* bp = p.bias + (p.shuf_C > 0 ? ncol % p.shuf_C : ncol);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ncol + j);
+                    for (int j = 0; j < 16; ++j) f[j] += __ldg(bp + j);
                 }
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.shuf_C > 0) {
+                    // ConvTranspose 2x2 stride 2 (see conv_tc.cu): the tap block of this column chunk selects the
+                    // output pixel of the 2x2 patch; shuf_C is a multiple of 16, every piece is 32-byte aligned
+                    const int tap = ncol / p.shuf_C, co = ncol - tap * p.shuf_C;
+                    const long long img = static_cast<long long>(tc.t) * p.B + tc.b0 + bi;
+                    const long long orow = (img * p.shuf_Hd + 2 * (tc.h0 + hi) + (tap >> 1) + p.shuf_oy) * p.shuf_Wd +
+                                           2 * (tc.w0 + wi) + (tap & 1) + p.shuf_ox;
+                    st_bf16x16(static_cast<__nv_bfloat16*>(p.dst0) + orow * p.shuf_C + co, f);
+                    continue;
                 }
                 const bool second = ncol >= p.split;
                 const long long off = second ? pix * p.ld1 + (ncol - p.split) : pix * p.ld0 + ncol;
@@ -462,8 +473,8 @@ static int launch_pair_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, cons
 }
 
 bool conv_tc2_supported(const ConvTcParams& p) {
-    // plain store epilogue only; the pixel-shuffle / statistics variants stay on the 1-CTA kernel
-    return p.shuf_C == 0 && p.stat_sum == nullptr && p.seq_T == 0 && p.N % 16 == 0;
+    // plain store and ConvTranspose pixel-shuffle epilogues; the fused-statistics variant stays on the 1-CTA kernel
+    return p.stat_sum == nullptr && p.seq_T == 0 && p.N % 16 == 0;
 }
 
 // Same contract as launch_conv_tc(.., epi, ..) for EPI_STORE problems conv_tc2_supported() accepts and for
