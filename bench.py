@@ -184,7 +184,7 @@ def run_reference_arm(args, out):
         "config": workload_config(args, batch_per_step=batch),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model,
                          "sample": f"{batch} sequence(s) per step (T={args.seq_len}, {args.size}x{args.size}, base_ch "
-                                   f"{args.base_ch} + skip LSTMs), fwd+bwd+AdamW, fp32, torch {torch.__version__} CPU "
+                                   f"{args.base_ch} + skip LSTMs), fwd + compute_loss + bwd + clip + AdamW, fp32, torch {torch.__version__} CPU "
                                    f"(oneDNN), {args.steps} timed steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -408,7 +408,7 @@ def run_b200_arm(args, out):
             cpu_model, _ = host_info()
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model,
-                "sample": f"{args.cpu_sample} sequence(s), 1 fwd+bwd+AdamW step of the same model and shapes "
+                "sample": f"{args.cpu_sample} sequence(s), 1 training step (fwd, compute_loss, bwd, clip, AdamW) of the same model and shapes "
                           f"(T={args.seq_len}, {args.size}x{args.size}), fp32, torch {torch.__version__} CPU "
                           f"(oneDNN) = the reference's own ATen operators (oracle/torch_port.py), {dt:.1f} s"}
         print(json.dumps(line), file=out, flush=True)
