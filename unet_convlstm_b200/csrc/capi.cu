@@ -12,6 +12,10 @@ using namespace b200;
 namespace b200 {
 int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
                     int ksize, float* dw, long long ldk, int koff, cudaStream_t stream);
+// wgrad_halo.cu: 64-channel 3x3 layers, source tile loaded once per pixel block
+bool wgrad_halo_supported(int Nz, int Csrc, int B, int H, int W, int ksize);
+int launch_wgrad_halo(const void* dz, int Nz, const void* src, int T, int B, int H, int W, float* dw, long long ldk,
+                      int koff, cudaStream_t stream);
 // wgrad_tc2.cu: narrow sources on a CTA pair (tcgen05 cta_group::2)
 bool wgrad_tc2_supported(int Nz, int Csrc, int ksize);
 int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, int ksize, float* dw,
@@ -230,6 +234,14 @@ extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, 
         set_last_error("b200_wgrad_tc: bad arguments");
         return B200_ERR_ARG;
     }
+    // B200_WGRAD_HALO (default 1): the halo kernel (wgrad_halo.cu) for the 64-channel 3x3 layers -- source tile
+    // loaded once per pixel block, taps as shifted MN-major descriptors: 820 -> 1090 TFLOP/s at Nz = 64, 64x64
+    static const int halo_mode = [] {
+        const char* e = getenv("B200_WGRAD_HALO");
+        return e ? atoi(e) : 1;
+    }();
+    if (halo_mode > 0 && (ldk % 4) == 0 && (koff % 4) == 0 && wgrad_halo_supported(Nz, Csrc, B, H, W, ksize))
+        return launch_wgrad_halo(dz, Nz, src, T, B, H, W, dw, ldk, koff, static_cast<cudaStream_t>(stream));
     // B200_WGRAD_2CTA: the CTA-pair kernel (wgrad_tc2.cu).  0 = never, 1 (default) = where it measured faster or
     // equal (profiles/r01_wgrad_2cta_ab.txt): every wide-source shape it supports (1.00-1.19x) and 64-channel sources
     // with dz >= 128 channels (912 -> 1100 TFLOP/s; at Nz = 64 both kernels sit at the L2 -> SM fill limit of the
