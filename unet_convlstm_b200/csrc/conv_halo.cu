@@ -36,7 +36,8 @@ struct ConvHaloParams {
     int RB;              // padded rows per activation box
     int tiles_per_img;   // ceil(H * P / 128)
     int num_m_tiles, num_n_tiles;
-    int chunks0, chunks; // 64-channel K chunks of source 0 / both sources
+    int kc;              // channels per K chunk: 64 (128-byte rows) or 16 (the 2-channel first layer padded to 16)
+    int chunks0, chunks; // K chunks of source 0 / both sources
     int SA, SB;          // activation / weight ring depths (SB unused when wres)
     int wres;            // weights resident in smem
     uint32_t a_stage_bytes, a_box_bytes, b_box_bytes;
@@ -136,7 +137,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 mbar_arrive_expect_tx(wfull, 9u * p.chunks * p.b_box_bytes);
                 uint32_t dst = b_base;
                 for (int tap = 0; tap < 9; ++tap)
-                    for (int c = 0; c < p.chunks; ++c, dst += p.b_box_bytes) tma_load_3d(dst, &tm_b, wfull, c * 64, 0, tap);
+                    for (int c = 0; c < p.chunks; ++c, dst += p.b_box_bytes) tma_load_3d(dst, &tm_b, wfull, c * p.kc, 0, tap);
             }
             __syncwarp();
         }
@@ -151,9 +152,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                     mbar_arrive_expect_tx(afull(sa), p.a_box_bytes);
                     const uint32_t dst = a_base + sa * p.a_stage_bytes;
                     if (c < p.chunks0)
-                        tma_load_5d(dst, &tm_a0, afull(sa), c * 64, -1, r0 - 1, img, 0);
+                        tma_load_5d(dst, &tm_a0, afull(sa), c * p.kc, -1, r0 - 1, img, 0);
                     else
-                        tma_load_5d(dst, &tm_a1, afull(sa), (c - p.chunks0) * 64, -1, r0 - 1, img, 0);
+                        tma_load_5d(dst, &tm_a1, afull(sa), (c - p.chunks0) * p.kc, -1, r0 - 1, img, 0);
                 }
                 __syncwarp();
                 if (++sa == p.SA) {
@@ -165,7 +166,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                         mbar_wait(bempty(sb), pb ^ 1u, p.err_flag, 120 + sb);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(bfull(sb), p.b_box_bytes);
-                            tma_load_3d(b_base + sb * p.b_box_bytes, &tm_b, bfull(sb), c * 64, n0, tap);
+                            tma_load_3d(b_base + sb * p.b_box_bytes, &tm_b, bfull(sb), c * p.kc, n0, tap);
                         }
                         __syncwarp();
                         if (++sb == p.SB) {
@@ -180,10 +181,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         // =================================== MMA issuer =====================================
         // converged warp, one elected lane issues (see the producer): back-to-back UTCHMMA
         const uint32_t idesc = make_idesc_bf16(H_BLOCK_M, BLOCK_N, 0, 0);
-        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);  // K-major, 128 B rows, 128B swizzle
+        // K-major operand rows of kc * 2 bytes: 128 B rows / 128B swizzle (kc = 64) or 32 B rows / 32B swizzle (kc = 16)
+        const uint32_t row_bytes = p.kc * 2;
+        const uint64_t desc_hi = make_smem_desc(0, 16, 8u * row_bytes, p.kc == 64 ? 2u : 6u);
+        const int mma_per_tap = p.kc / 16;
         const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4, b_lo0 = (b_base & 0x3FFFFu) >> 4;
         const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_box_lo = p.b_box_bytes >> 4;
-        const uint32_t row_lo = 128u >> 4;  // one padded position = one 128-byte row
+        const uint32_t row_lo = row_bytes >> 4;  // one padded position = one operand row
         if (p.wres) {
             mbar_wait(wfull, 0, p.err_flag, 250);
             tc_fence_after();
@@ -214,9 +218,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                                 const uint64_t adesc = desc_hi | a_row;
                                 const uint64_t bdesc = desc_hi | b_lo;
                                 umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                                if (mma_per_tap == 4) {
+                                    umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                                    umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                                    umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                                }
                                 accum = 1u;
                             }
                         }
@@ -234,9 +240,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                                 const uint64_t adesc = desc_hi | a_row;
                                 const uint64_t bdesc = desc_hi | (b_lo0 + sb * b_box_lo);
                                 umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                                if (mma_per_tap == 4) {
+                                    umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                                    umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                                    umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                                }
                                 umma_commit(bempty(sb));
                             }
                             __syncwarp();
@@ -422,7 +430,11 @@ static constexpr int H_SMEM_LIMIT = 227 * 1024;
 // Geometry / shared-memory plan; returns false if the halo kernel cannot (or should not) run this problem.
 static bool plan_halo(int IMG, int H, int W, int C0, int C1, int N, int ksize, int block_n, ConvHaloParams* p,
                       int* smem_bytes) {
-    if (ksize != 3 || C0 <= 0 || C0 % 64 != 0 || C1 % 64 != 0 || N % 16 != 0 || W + 2 > 256 || W < 4) return false;
+    if (ksize != 3 || C0 <= 0 || N % 16 != 0 || W + 2 > 256 || W < 4) return false;
+    // 64-channel K chunks, or the single 16-channel chunk of the zero-padded first layer
+    const int kc = (C0 == 16 && C1 == 0) ? 16 : 64;
+    if (C0 % kc != 0 || C1 % kc != 0) return false;
+    p->kc = kc;
     p->IMG = IMG; p->H = H; p->W = W; p->C0 = C0; p->C1 = C1; p->N = N;
     p->P = W + 2;
     p->RB = 3 + (129 + p->P - 1) / p->P;
@@ -430,11 +442,11 @@ static bool plan_halo(int IMG, int H, int W, int C0, int C1, int N, int ksize, i
     p->tiles_per_img = (H * p->P + H_BLOCK_M - 1) / H_BLOCK_M;
     p->num_m_tiles = IMG * p->tiles_per_img;
     p->num_n_tiles = (N + block_n - 1) / block_n;
-    p->chunks0 = C0 / 64;
-    p->chunks = (C0 + C1) / 64;
-    p->a_box_bytes = static_cast<uint32_t>(p->RB) * p->P * 128u;
+    p->chunks0 = C0 / kc;
+    p->chunks = (C0 + C1) / kc;
+    p->a_box_bytes = static_cast<uint32_t>(p->RB) * p->P * static_cast<uint32_t>(kc * 2);
     p->a_stage_bytes = (p->a_box_bytes + 1023u) & ~1023u;
-    p->b_box_bytes = static_cast<uint32_t>(block_n) * 128u;
+    p->b_box_bytes = static_cast<uint32_t>(block_n) * static_cast<uint32_t>(kc * 2);
     const int fixed = 1024 + 256 + 8 * block_n * 4;  // alignment slack + barriers + BatchNorm partial sums
     // resident weights if they leave room for >= 2 activation stages (single N tile only)
     const long long wbytes = 9LL * p->chunks * p->b_box_bytes;
@@ -500,20 +512,20 @@ int launch_conv_halo(const void* src0, const void* src1, const void* wpacked, in
     {
         const uint64_t dims[5] = {uint64_t(C0), uint64_t(W), uint64_t(H), uint64_t(IMG), 1};
         const uint64_t str[4] = {uint64_t(C0), uint64_t(C0) * W, uint64_t(C0) * W * H, uint64_t(C0) * W * H * IMG};
-        const uint32_t box[5] = {64u, uint32_t(p.P), uint32_t(p.RB), 1u, 1u};
+        const uint32_t box[5] = {uint32_t(p.kc), uint32_t(p.P), uint32_t(p.RB), 1u, 1u};
         int rc = make_tmap_5d(&ta0, src0, dims, str, box);
         if (rc != B200_OK) return rc;
     }
     if (C1 > 0) {
         const uint64_t dims[5] = {uint64_t(C1), uint64_t(W), uint64_t(H), uint64_t(IMG), 1};
         const uint64_t str[4] = {uint64_t(C1), uint64_t(C1) * W, uint64_t(C1) * W * H, uint64_t(C1) * W * H * IMG};
-        const uint32_t box[5] = {64u, uint32_t(p.P), uint32_t(p.RB), 1u, 1u};
+        const uint32_t box[5] = {uint32_t(p.kc), uint32_t(p.P), uint32_t(p.RB), 1u, 1u};
         int rc = make_tmap_5d(&ta1, src1, dims, str, box);
         if (rc != B200_OK) return rc;
     } else {
         ta1 = ta0;
     }
-    int rc = make_w_tmap(&tb, wpacked, C0 + C1, N, 9, 64, block_n);
+    int rc = make_w_tmap(&tb, wpacked, C0 + C1, N, 9, p.kc, block_n);
     if (rc != B200_OK) return rc;
     switch (block_n) {
         case 256: return launch_halo_impl<256>(ta0, ta1, tb, p, smem, stream);
