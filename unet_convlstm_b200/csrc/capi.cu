@@ -14,8 +14,8 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
                     int ksize, float* dw, long long ldk, int koff, cudaStream_t stream);
 // wgrad_halo.cu: 64-channel 3x3 layers, source tile loaded once per pixel block
 bool wgrad_halo_supported(int Nz, int Csrc, int B, int H, int W, int ksize);
-int launch_wgrad_halo(const void* dz, int Nz, const void* src, int T, int B, int H, int W, float* dw, long long ldk,
-                      int koff, cudaStream_t stream);
+int launch_wgrad_halo(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, float* dw,
+                      long long ldk, int koff, cudaStream_t stream);
 // wgrad_tc2.cu: narrow sources on a CTA pair (tcgen05 cta_group::2)
 bool wgrad_tc2_supported(int Nz, int Csrc, int ksize);
 int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, int ksize, float* dw,
@@ -241,7 +241,7 @@ extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, 
         return e ? atoi(e) : 1;
     }();
     if (halo_mode > 0 && (ldk % 4) == 0 && (koff % 4) == 0 && wgrad_halo_supported(Nz, Csrc, B, H, W, ksize))
-        return launch_wgrad_halo(dz, Nz, src, T, B, H, W, dw, ldk, koff, static_cast<cudaStream_t>(stream));
+        return launch_wgrad_halo(dz, Nz, src, Csrc, T, B, H, W, dw, ldk, koff, static_cast<cudaStream_t>(stream));
     // B200_WGRAD_2CTA: the CTA-pair kernel (wgrad_tc2.cu).  0 = never, 1 (default) = where it measured faster or
     // equal (profiles/r01_wgrad_2cta_ab.txt): every wide-source shape it supports (1.00-1.19x) and 64-channel sources
     // with dz >= 128 channels (912 -> 1100 TFLOP/s; at Nz = 64 both kernels sit at the L2 -> SM fill limit of the

@@ -14,6 +14,11 @@
 // Source traffic per 128 pixels drops from 18 x 8 KB to one 33 KB box; the dz box is shared by all nine taps
 // (five M = 128 accumulators of 64 columns in TMEM).
 //
+// 16-channel sources (the UNet's first layer: 2 input channels zero-padded to 16): rows of 32 bytes, 32-byte swizzle;
+// the M = 128 operand has eight 16-channel slots, three of which hold the taps (0,kx) (1,kx) (2,kx) of one kx --
+// equally spaced by one tile row pitch, which is what a single leading-dimension offset can express -- so three
+// MMAs (kx = 0, 1, 2) per K step; the other five slots read rows past the taps and are never stored.
+//
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue (transposed fp32
 // stores / red.global.add for split-K, as wgrad_tc.cu).
 #include "common.cuh"
@@ -30,6 +35,7 @@ static constexpr int WH_DZ_BYTES = WH_RB * 128;
 struct WgradHaloParams {
     int T, B, H, W;
     int Nz;
+    int Cs;            // source channels: 64 or 16
     int Ht;            // image rows per block = 128 / W
     int P;             // padded tile width W + 2
     int blocks_per_img;
@@ -129,10 +135,14 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
         const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
-        const uint32_t row_lo = 128u >> 4;                      // one pixel row of the tile = 128 bytes
-        // A descriptors: per tap pair the leading-dimension offset is the distance between the two taps
-        const uint64_t hiA_near = make_smem_desc(0, 128, 1024, 2);            // (ky, kx) , (ky, kx + 1)
-        const uint64_t hiA_wrap = make_smem_desc(0, p.W * 128u, 1024, 2);     // (ky, 2)  , (ky + 1, 0)
+        const uint32_t row_lo = 128u >> 4;                      // one pixel row of the dz tile = 128 bytes
+        const uint32_t srow = p.Cs * 2;                         // one pixel row of the source tile: 128 or 32 bytes
+        const uint32_t srow_lo = srow >> 4;
+        const uint32_t ltS = p.Cs == 64 ? 2u : 6u;              // 128-byte / 32-byte swizzle
+        // A descriptors: the leading-dimension offset is the distance between the stacked taps
+        const uint64_t hiA_near = make_smem_desc(0, srow, 8u * srow, ltS);            // (ky, kx) , (ky, kx + 1)
+        const uint64_t hiA_wrap = make_smem_desc(0, p.W * srow, 8u * srow, ltS);      // (ky, 2)  , (ky + 1, 0)
+        const uint64_t hiA_col = make_smem_desc(0, p.P * srow, 8u * srow, ltS);       // (0, kx), (1, kx), (2, kx), ...
         const uint64_t hiB = make_smem_desc(0, WH_DZ_BYTES, 1024, 2);
         const int steps_per_row = p.W >> 4;
         const uint32_t smem_lo = (smem_base & 0x3FFFFu) >> 4;
@@ -155,12 +165,19 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
                     for (int ks = 0; ks < WH_RB / 16; ++ks) {
                         const uint64_t bdesc = hiB | (dz_lo + ks * 16 * row_lo);
                         const uint32_t row0 = hl * p.P + wstep * 16;  // tile row of tap (0, 0) for this K step
-                        // tap pairs: (0,0)(0,1) | (0,2)(1,0) | (1,1)(1,2) | (2,0)(2,1) | (2,2)(-)
-                        umma_bf16(tmem_base + 0 * 64, hiA_near | (src_lo + (row0) * row_lo), bdesc, idesc, accum);
-                        umma_bf16(tmem_base + 1 * 64, hiA_wrap | (src_lo + (row0 + 2) * row_lo), bdesc, idesc, accum);
-                        umma_bf16(tmem_base + 2 * 64, hiA_near | (src_lo + (row0 + p.P + 1) * row_lo), bdesc, idesc, accum);
-                        umma_bf16(tmem_base + 3 * 64, hiA_near | (src_lo + (row0 + 2 * p.P) * row_lo), bdesc, idesc, accum);
-                        umma_bf16(tmem_base + 4 * 64, hiA_near | (src_lo + (row0 + 2 * p.P + 2) * row_lo), bdesc, idesc, accum);
+                        if (p.Cs == 64) {
+                            // tap pairs: (0,0)(0,1) | (0,2)(1,0) | (1,1)(1,2) | (2,0)(2,1) | (2,2)(-)
+                            umma_bf16(tmem_base + 0 * 64, hiA_near | (src_lo + (row0) * srow_lo), bdesc, idesc, accum);
+                            umma_bf16(tmem_base + 1 * 64, hiA_wrap | (src_lo + (row0 + 2) * srow_lo), bdesc, idesc, accum);
+                            umma_bf16(tmem_base + 2 * 64, hiA_near | (src_lo + (row0 + p.P + 1) * srow_lo), bdesc, idesc, accum);
+                            umma_bf16(tmem_base + 3 * 64, hiA_near | (src_lo + (row0 + 2 * p.P) * srow_lo), bdesc, idesc, accum);
+                            umma_bf16(tmem_base + 4 * 64, hiA_near | (src_lo + (row0 + 2 * p.P + 2) * srow_lo), bdesc, idesc, accum);
+                        } else {
+                            // tap columns: slots 0..2 of the M operand = (0,kx) (1,kx) (2,kx), one MMA per kx
+                            umma_bf16(tmem_base + 0 * 64, hiA_col | (src_lo + (row0) * srow_lo), bdesc, idesc, accum);
+                            umma_bf16(tmem_base + 1 * 64, hiA_col | (src_lo + (row0 + 1) * srow_lo), bdesc, idesc, accum);
+                            umma_bf16(tmem_base + 2 * 64, hiA_col | (src_lo + (row0 + 2) * srow_lo), bdesc, idesc, accum);
+                        }
                         accum = 1u;
                         if (++wstep == steps_per_row) {
                             wstep = 0;
@@ -184,7 +201,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
         // =================================== epilogue =======================================
         const int q = static_cast<int>(threadIdx.x >> 5) - 4;
         const int r = q * 32 + lane;
-        const int gi = r >> 6, c = r & 63;  // row = (tap within the pair, source channel)
+        // accumulator row = (slot, source channel): 64 channels -> 2 slots (the tap pair), 16 channels -> 8 slots of
+        // which 0..2 are the taps (ky = slot) of the group's kx
+        const int gi = p.Cs == 64 ? (r >> 6) : (r >> 4);
+        const int c = p.Cs == 64 ? (r & 63) : (r & 15);
+        const int ngroups = p.Cs == 64 ? WH_GROUPS : 3;
         uint32_t pt = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
             const int split = unit / p.s_tiles;
@@ -192,9 +213,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
             mbar_wait(tfull, pt, p.err_flag, 800);
             pt ^= 1u;
             tc_fence_after();
-            for (int g = 0; g < WH_GROUPS; ++g) {
-                const int tp = 2 * g + gi;
-                const bool valid = tp < 9;
+            for (int g = 0; g < ngroups; ++g) {
+                const int tp = p.Cs == 64 ? 2 * g + gi : gi * 3 + g;
+                const bool valid = p.Cs == 64 ? tp < 9 : gi < 3;
                 float* row = p.dw + (static_cast<long long>(valid ? tp : 0) * p.Nz + s0) * p.ldk + p.koff + c;
                 const uint32_t t_row = tmem_base + g * 64 + (uint32_t(q * 32) << 16);
 #pragma unroll 1
@@ -228,26 +249,26 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
 }
 
 bool wgrad_halo_supported(int Nz, int Csrc, int B, int H, int W, int ksize) {
-    if (Csrc != 64 || ksize != 3 || Nz % 64 != 0) return false;
+    if ((Csrc != 64 && Csrc != 16) || ksize != 3 || Nz % 64 != 0) return false;
     if (!(W == 16 || W == 32 || W == 64 || W == 128)) return false;
     const int Ht = WH_RB / W;
     return H % Ht == 0 && B > 0;
 }
 
-int launch_wgrad_halo(const void* dz, int Nz, const void* src, int T, int B, int H, int W, float* dw, long long ldk,
-                      int koff, cudaStream_t stream) {
-    if (!wgrad_halo_supported(Nz, 64, B, H, W, 3)) {
+int launch_wgrad_halo(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, float* dw,
+                      long long ldk, int koff, cudaStream_t stream) {
+    if (!wgrad_halo_supported(Nz, Csrc, B, H, W, 3)) {
         set_last_error("wgrad_halo: shape not supported");
         return B200_ERR_SHAPE;
     }
     WgradHaloParams p = {};
-    p.T = T; p.B = B; p.H = H; p.W = W; p.Nz = Nz;
+    p.T = T; p.B = B; p.H = H; p.W = W; p.Nz = Nz; p.Cs = Csrc;
     p.Ht = WH_RB / W;
     p.P = W + 2;
     p.blocks_per_img = H / p.Ht;
     p.num_rblocks = T * B * p.blocks_per_img;
     p.s_tiles = Nz / 64;
-    p.src_bytes = static_cast<uint32_t>(p.P) * (p.Ht + 2) * 128u;
+    p.src_bytes = static_cast<uint32_t>(p.P) * (p.Ht + 2) * static_cast<uint32_t>(Csrc * 2);
     p.src_stage_bytes = (p.src_bytes + 1023u) & ~1023u;
     const int nsm = num_sms();
     int max_splits = (p.num_rblocks + 3) / 4;
@@ -271,7 +292,7 @@ int launch_wgrad_halo(const void* dz, int Nz, const void* src, int T, int B, int
     CUtensorMap tz, ts;
     int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, 64, W, p.Ht, 1);
     if (rc != B200_OK) return rc;
-    rc = make_act_tmap(&ts, src, 64, W, H, B, T, 64, p.P, p.Ht + 2, 1);
+    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, Csrc, p.P, p.Ht + 2, 1);
     if (rc != B200_OK) return rc;
     const int stage_bytes = static_cast<int>(p.src_stage_bytes + WH_DZ_BYTES);
     p.stages = (227 * 1024 - 1280) / stage_bytes;
