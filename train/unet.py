@@ -154,6 +154,11 @@ class Down(nn.Module):
     def _seq(self, x):
         return self.net[1]._seq(Fn.MaxPool2.apply(x))
 
+    def _seq_fork(self, x):
+        """(x for the skip connection, Down(x)): the two gradients of x are summed inside the max-pool backward."""
+        skip, pooled = Fn.PoolFork.apply(x)
+        return skip, self.net[1]._seq(pooled)
+
     def forward(self, x):
         _require_cuda(x, "Down")
         return _to_nchw(self._seq(_to_nhwc(x)))
@@ -231,10 +236,10 @@ class TemporalUNetDualView(nn.Module):
 
     def _encode(self, x):
         x0 = self.inc._seq(x)
-        x1 = self.down1._seq(x0)
-        x2 = self.down2._seq(x1)
-        x3 = self.down3._seq(x2)
-        xb = self.bottleneck._seq(x3)
+        x0, x1 = self.down1._seq_fork(x0)
+        x1, x2 = self.down2._seq_fork(x1)
+        x2, x3 = self.down3._seq_fork(x2)
+        x3, xb = self.bottleneck._seq_fork(x3)
         if self.use_attention:
             T, B, H, W, C = xb.shape
             a = self.attention(xb.reshape(T * B, H, W, C).permute(0, 3, 1, 2).float())

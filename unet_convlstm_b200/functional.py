@@ -172,6 +172,32 @@ class MaxPool2(torch.autograd.Function):
         return ops.maxpool2_bwd(x, _c(dy).to(x.dtype))
 
 
+class PoolFork(torch.autograd.Function):
+    """(skip, pooled) = (x, maxpool2(x)) for an encoder output that feeds both the next Down stage and a skip
+    connection (unet.py:179-182 -> :196-202).  Autograd would sum the two gradients of x with an extra element-wise
+    pass (2 reads + 1 write of the largest activation tensors); here the max-pool backward ADDS its routed gradient
+    into the skip gradient in place (1 extra read)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = ops.maxpool2_fwd(x)
+        ctx.save_for_backward(x)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, g_skip, g_pool):
+        (x,) = ctx.saved_tensors
+        if g_pool is None:
+            return g_skip
+        g_pool = _c(g_pool).to(x.dtype)
+        if g_skip is None:
+            return ops.maxpool2_bwd(x, g_pool)
+        if g_skip.dtype != x.dtype or not g_skip.is_contiguous():
+            g_skip = g_skip.to(x.dtype).contiguous()
+        return ops.maxpool2_bwd(x, g_pool, accumulate_into=g_skip)
+
+
 # ------------------------------------------------------------------------------------------------
 # ConvTranspose2d(k=2, stride=2) + F.pad to the skip size (Up, unet.py:90-97)
 # ------------------------------------------------------------------------------------------------

@@ -364,10 +364,16 @@ def maxpool2_fwd(x):
     return y
 
 
-def maxpool2_bwd(x, dy):
+def maxpool2_bwd(x, dy, accumulate_into=None):
+    """dx = routing of dy to the maxima of x; with accumulate_into (a contiguous tensor like x) the routed gradient is
+    ADDED to it in place -- the other gradient of a skip connection -- and it is returned."""
     _chk(x, "x"), _chk(dy, "dy")
     T, B, H, W, C = x.shape
-    dx = torch.empty_like(x)
+    if accumulate_into is not None:
+        _chk(accumulate_into, "accumulate_into")
+        _lib.call("b200_maxpool2_bwd", _p(x), _p(dy), _p(accumulate_into), T * B, H, W, C, 1, _f32(x), _st())
+        return accumulate_into
+    dx = (torch.empty_like if (H % 2 == 0 and W % 2 == 0) else torch.zeros_like)(x)
     _lib.call("b200_maxpool2_bwd", _p(x), _p(dy), _p(dx), T * B, H, W, C, 0, _f32(x), _st())
     return dx
 
