@@ -198,7 +198,7 @@ def workload_config(args, batch_per_step=None):
         "batch_per_gpu": args.batch if batch_per_step is None else batch_per_step, "seq_len": args.seq_len,
         "image": args.size, "base_ch": args.base_ch, "use_skip_lstm": True, "precision": args.precision,
         "step": "the reference's training step (main.py:94-108): forward, compute_loss (weighted L1 + gradient loss, "
-                "masked), backward, clip_grad_norm_(1.0), AdamW(fused) update; gradient all-reduce overlapped when N > 1",
+                "masked), backward, clip_grad_norm_(1.0) + AdamW (multi-tensor kernels) update; gradient all-reduce overlapped when N > 1",
         "parallelism": f"dp{args.gpus}",
         "l2": "per-step working set (tens of GB of activations, 168 MB of inputs) far exceeds the 126 MB L2",
     }
@@ -228,7 +228,14 @@ def run_b200_arm(args, out):
     model = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).to(dev)
     model.train()
     use_graph = bool(args.graph) and world == 1
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=use_graph)
+    # B200_OPTIM=torch: torch's foreach clip_grad_norm_ + fused AdamW instead of the multi-tensor kernels of
+    # unet_convlstm_b200/optim.py (A/B switch; a CUDA graph needs torch's capturable step counter)
+    own_optim = os.environ.get("B200_OPTIM", "b200") != "torch" and not use_graph
+    if own_optim:
+        from unet_convlstm_b200.optim import AdamW as B200AdamW
+        opt = B200AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=use_graph)
     reducer = GradReducer(model.parameters()) if world > 1 else None
 
     from unet_convlstm_b200.loss import compute_loss
@@ -246,7 +253,9 @@ def run_b200_arm(args, out):
         loss.backward()
         if reducer is not None:
             reducer.finish()
-        if with_opt:
+        if with_opt and own_optim:
+            opt.step(clip_max_norm=1.0)        # global-norm clip folded into the multi-tensor AdamW kernel
+        elif with_opt:
             torch.nn.utils.clip_grad_norm_(params, 1.0)
             opt.step()
         return loss

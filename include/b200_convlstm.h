@@ -203,6 +203,31 @@ int b200_wl1_grad_loss_fwd(const float* y_pred, const float* y, const float* mas
 int b200_wl1_grad_loss_bwd(const float* y_pred, const float* y, const float* mask, long long IMG, int H, int W,
                            const double* sums, const float* grad_out, float* d_y_pred, void* stream);
 
+/* Error metrics of the reference's train / evaluate loops (main.py:110-145, :166-199): both maps are de-normalised
+ * like NPZSequenceDataset.denormalize (unet.py:306-327; transform 0 = identity, 1 = asinh, 2 = signed_log) and
+ * acc[0..3] += {sum |d|, sum d^2, sum d, count} over the pixels with mask != 0 (mask == NULL: all pixels).
+ * y_pred / y / mask: fp32 [n]; acc: fp64 [4] on the device, zeroed by the caller at the start of an epoch and read
+ * once at its end (MAE = acc0/acc3, RMSE = sqrt(acc1/acc3), ME = acc2/acc3). */
+int b200_denorm_metrics_accum(const float* y_pred, const float* y, const float* mask, long long n, int transform,
+                              double trans_min, double trans_max, double y_scale, double* acc, void* stream);
+
+/* Gradient clipping + AdamW of the reference's step (main.py:106 clip_grad_norm_(params, 1.0); main.py:275
+ * torch.optim.AdamW) over a LIST of fp32 tensors.  The pointer arrays (params, grads, ...) and numel live in HOST
+ * memory and hold n device pointers / element counts; they are copied into the kernel parameters (48 tensors per
+ * launch), so they may be freed as soon as the call returns.
+ *   b200_grad_sqnorm_multi : *sqnorm (fp64, device) = sum over all tensors of g^2
+ *   b200_grad_clip_multi   : g *= min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) in place (clip_grad_norm_ semantics)
+ *   b200_adamw_multi       : decoupled weight decay + Adam moments + bias-corrected update, torch.optim.AdamW
+ *                            arithmetic (amsgrad = False, maximize = False); `step` is the 1-based update count.
+ *                            sqnorm != NULL and max_norm > 0 folds the clip coefficient into the gradient read
+ *                            (the gradients themselves are left unscaled). */
+int b200_grad_sqnorm_multi(int n, const void* const* grads, const long long* numel, double* sqnorm, void* stream);
+int b200_grad_clip_multi(int n, void* const* grads, const long long* numel, const double* sqnorm, float max_norm,
+                         void* stream);
+int b200_adamw_multi(int n, void* const* params, const void* const* grads, void* const* exp_avg,
+                     void* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, long long step, const double* sqnorm, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -739,3 +739,151 @@ def test_first_layer_direct_kernels_vs_simt(T, B, H, W, cin, N):
     _lib.call("b200_wgrad_simt", dzf.data_ptr(), N, xf.data_ptr(), 16, T * B, H, W, 3, refw.data_ptr(), 16, 0, 1, st)
     refw = refw[:, :, :cin].permute(1, 2, 0).reshape(N, cin, 3, 3)
     assert rel(_np(dw), _np(refw)) < 1e-4
+
+
+class _Preset(torch.nn.Module):
+    """Stand-in model of tests/golden/make_golden_metrics.py: returns preset predictions as a list of T frames."""
+
+    def __init__(self, preds):
+        super().__init__()
+        self.preds, self.i = preds, 0
+
+    def forward(self, x):
+        p = self.preds[self.i]
+        self.i += 1
+        return [p[:, t] for t in range(p.shape[1])], None
+
+
+def test_epoch_loop_matches_reference_evaluate(golden_dir):
+    """unet_convlstm_b200.loop.evaluate (fused loss + on-device metric accumulators, host batches prefetched on a
+    side stream) against the fixture produced by the reference's own main.evaluate (main.py:150-204)."""
+    import types
+    from unet_convlstm_b200 import loop
+    z = np.load(os.path.join(golden_dir, "metrics_main_evaluate.npz"))
+    for tr in ("asinh", "signed_log", "none"):
+        tmin, tmax, scale = z[f"{tr}.params"]
+        ds = types.SimpleNamespace(trans_min=tmin, trans_max=tmax, y_scale=scale, y_transform=tr)
+        host = [tuple(torch.from_numpy(z[f"{tr}.b{i}.{k}"]) for k in ("x", "y", "mask")) for i in range(3)]
+        preds = [_cuda(z[f"{tr}.b{i}.pred"]) for i in range(3)]
+        for use in (True, False):
+            got = loop.evaluate(_Preset(preds), host, "cuda", ds, use_mask=use)
+            np.testing.assert_allclose(got, z[f"{tr}.use{int(use)}.result"], rtol=3e-6, atol=3e-7,
+                                       err_msg=f"{tr} use={use}")
+    ds = types.SimpleNamespace(trans_min=z["asinh.params"][0], trans_max=z["asinh.params"][1],
+                               y_scale=z["asinh.params"][2], y_transform="asinh")
+    x, y, m = (_cuda(z[f"asinh.b1.{k}"]) for k in ("x", "y", "mask"))          # device batches are taken as they are
+    got = loop.evaluate(_Preset([_cuda(z["asinh.b1.pred"])]), [(x, y, torch.zeros_like(m))], "cuda", ds)
+    np.testing.assert_allclose(got, z["empty.result"], rtol=3e-6, atol=3e-7)
+
+
+def test_train_one_epoch_matches_stepwise_host_loop():
+    """loop.train_one_epoch against the reference's loop structure restated step by step (main.py:77-145:
+    per-step loss.item(), host-side NumPy metric lists through the oracle) on the same model, data and seeds."""
+    import copy
+    import types
+    import unet_convlstm_b200 as pkg
+    from oracle import metrics_oracle as MO
+    from train.unet import TemporalUNetDualView
+    from unet_convlstm_b200 import loop
+    from unet_convlstm_b200.loss import compute_loss
+    pkg.set_precision("fp32")
+    try:
+        torch.manual_seed(11)
+        m1 = TemporalUNetDualView(base_ch=4, use_skip_lstm=True).cuda()
+        m2 = copy.deepcopy(m1)
+        rng = np.random.default_rng(5)
+        batches = []
+        for b in (3, 2, 3):
+            x = torch.from_numpy((rng.random((b, 3, 2, 16, 16)) * 2).astype(np.float32))
+            y = torch.from_numpy(np.clip(rng.standard_normal((b, 3, 1, 16, 16)), -1, 1).astype(np.float32))
+            batches.append((x, y, (x[:, :, 0:1] > 1.1).float()))
+        ds = types.SimpleNamespace(trans_min=-1.05, trans_max=1.17, y_scale=6.0, y_transform="asinh")
+        o1 = torch.optim.AdamW(m1.parameters(), lr=1e-3)
+        o2 = torch.optim.AdamW(m2.parameters(), lr=1e-3)
+        got = loop.train_one_epoch(m1, batches, o1, "cuda", ds)
+        m2.train()
+        tot, n, seen = 0.0, 0, []
+        for x, y, mask in batches:
+            x, y, mask = x.cuda(), y.cuda(), mask.cuda()
+            o2.zero_grad(set_to_none=True)
+            out, _ = m2(x)
+            yp = torch.stack(out, dim=1)
+            loss = compute_loss(yp, y, mask, True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m2.parameters(), 1.0)
+            o2.step()
+            tot += loss.item() * x.size(0)
+            n += x.size(0)
+            seen.append((_np(yp), _np(y), _np(mask)))
+        ref = (tot / n, *MO.epoch_metrics(seen, ds.trans_min, ds.trans_max, ds.y_scale, "asinh"))
+        np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-6)
+        for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+            assert rel2(_np(a), _np(b)) < 1e-3, k
+    finally:
+        pkg.set_precision("bf16")
+
+
+def _optim_problem(n_tensors, seed):
+    rng = np.random.default_rng(seed)
+    sizes = [int(s) for s in rng.integers(1, 9000, n_tensors)]
+    sizes[0], sizes[1], sizes[2] = 4096 * 3, 4096 * 2 + 5, 1            # whole chunks, ragged tail, single element
+    ps = [rng.standard_normal(s) for s in sizes]
+    gs = [[rng.standard_normal(s) * (10.0 if it == 0 else 0.01) for s in sizes] for it in range(4)]
+    return ps, gs
+
+
+@pytest.mark.parametrize("n_tensors,clip", [(7, 1.0), (101, 1.0), (101, None)])
+def test_multi_tensor_clip_adamw_matches_torch(n_tensors, clip):
+    """unet_convlstm_b200.optim (b200_grad_sqnorm_multi / b200_grad_clip_multi / b200_adamw_multi) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW in fp64 on the CPU -- the reference's own calls
+    (main.py:106, :275).  Covers > 48 tensors (several launches), unaligned storage offsets, a clipping and a
+    non-clipping step, the fused clip-in-update form and the state_dict round trip into torch.optim.AdamW."""
+    from unet_convlstm_b200 import optim
+    ps, gs = _optim_problem(n_tensors, n_tensors)
+    ref_p = [torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in ps]
+    pool = torch.zeros(sum(p.size + 3 for p in ps), device="cuda")
+    mine, fused, off = [], [], 0
+    for i, p in enumerate(ps):
+        off += i % 4                                                     # storage offsets that are not 16-byte aligned
+        v = pool[off:off + p.size]
+        v.copy_(torch.from_numpy(p))
+        off += p.size
+        mine.append(torch.nn.Parameter(v))
+        fused.append(torch.nn.Parameter(torch.from_numpy(p).float().cuda()))
+    kw = dict(lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.05)
+    o_ref, o_mine, o_fused = torch.optim.AdamW(ref_p, **kw), optim.AdamW(mine, **kw), optim.AdamW(fused, **kw)
+    for it in range(4):
+        for lst in (ref_p, mine, fused):
+            for p, g in zip(lst, gs[it]):
+                p.grad = torch.from_numpy(g).to(p.dtype).to(p.device)
+        if clip is not None:
+            n_ref = torch.nn.utils.clip_grad_norm_(ref_p, clip)
+            n_mine = optim.clip_grad_norm_(mine, clip)
+            assert abs(float(n_mine) - float(n_ref)) <= 2e-6 * float(n_ref)
+            for a, b in zip(mine, ref_p):
+                assert rel2(_np(a.grad), b.grad.numpy()) < 1e-6
+        o_ref.step(), o_mine.step(), o_fused.step(clip_max_norm=clip)
+        for a, f, b in zip(mine, fused, ref_p):
+            ref = b.detach().numpy()
+            tol = 2e-6 * (it + 1)
+            assert np.abs(_np(a) - ref).max() <= tol * max(1.0, np.abs(ref).max()), it
+            assert np.abs(_np(f) - ref).max() <= tol * max(1.0, np.abs(ref).max()), it
+    for a, b in zip(mine, ref_p):
+        assert rel2(_np(o_mine.state[a]["exp_avg"]), o_ref.state[b]["exp_avg"].numpy()) < 1e-5
+        assert rel2(_np(o_mine.state[a]["exp_avg_sq"]), o_ref.state[b]["exp_avg_sq"].numpy()) < 1e-5
+        assert float(o_mine.state[a]["step"]) == 4.0
+    # the state moves into torch.optim.AdamW and both continue identically
+    o_t = torch.optim.AdamW(fused, **kw)
+    import copy
+    o_t.load_state_dict(copy.deepcopy(o_fused.state_dict()))         # load_state_dict shares the tensors otherwise
+    before = [p.detach().clone() for p in fused]
+    for p, g in zip(fused, gs[0]):
+        p.grad = torch.from_numpy(g).float().cuda()
+    o_t.step()
+    after_t = [p.detach().clone() for p in fused]
+    with torch.no_grad():
+        for p, b in zip(fused, before):
+            p.copy_(b)
+    o_fused.step()
+    for a, b in zip(fused, after_t):
+        assert np.abs(_np(a) - _np(b)).max() <= 2e-6 * max(1.0, float(b.abs().max()))

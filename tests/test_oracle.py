@@ -212,3 +212,25 @@ def test_loss_oracle_matches_reference_compute_loss(golden_dir):
             loss, grad = LO.compute_loss(z[f"{name}.yp"], z[f"{name}.y"], mask, use_mask=(tag != "ignored"))
             assert abs(loss - float(z[f"{name}.{tag}.loss"])) <= 1e-12 * max(1.0, abs(loss)), (name, tag)
             np.testing.assert_allclose(grad, z[f"{name}.{tag}.grad"], rtol=1e-10, atol=1e-14, err_msg=f"{name}.{tag}")
+
+
+def test_metrics_oracle_matches_reference_evaluate(golden_dir):
+    """oracle/metrics_oracle.py (+ the loss oracle) against the fixture produced by the reference's own
+    main.evaluate with the reference's NPZSequenceDataset.denormalize (tests/golden/make_golden_metrics.py)."""
+    from oracle import loss_oracle as LO
+    from oracle import metrics_oracle as MO
+    z = np.load(os.path.join(golden_dir, "metrics_main_evaluate.npz"))
+    for tr in ("asinh", "signed_log", "none"):
+        tmin, tmax, scale = z[f"{tr}.params"]
+        batches = [(z[f"{tr}.b{i}.pred"], z[f"{tr}.b{i}.y"], z[f"{tr}.b{i}.mask"]) for i in range(3)]
+        for use in (True, False):
+            ref = z[f"{tr}.use{int(use)}.result"]
+            mae, rmse, me = MO.epoch_metrics(batches, tmin, tmax, scale, tr, use_mask=use)
+            tot = sum(LO.compute_loss(p, y, m, use_mask=use)[0] * p.shape[0] for p, y, m in batches)
+            n = sum(p.shape[0] for p, _, _ in batches)
+            # the reference accumulates float32 losses (.item()) and float32/64 NumPy lists
+            np.testing.assert_allclose([tot / n, mae, rmse, me], ref, rtol=2e-6, atol=2e-7, err_msg=f"{tr} use={use}")
+    p, y, m = z["asinh.b1.pred"], z["asinh.b1.y"], np.zeros_like(z["asinh.b1.mask"])
+    tmin, tmax, scale = z["asinh.params"]
+    assert MO.epoch_metrics([(p, y, m)], tmin, tmax, scale, "asinh") == (0.0, 0.0, 0.0)
+    assert tuple(z["empty.result"][1:]) == (0.0, 0.0, 0.0)

@@ -1,0 +1,231 @@
+// Gradient clipping + AdamW of the reference's training step (main.py:106 `clip_grad_norm_(params, 1.0)`,
+// main.py:275 `torch.optim.AdamW`) as multi-tensor kernels: ONE pass over all gradients for the global norm and ONE
+// pass over {param, grad, exp_avg, exp_avg_sq} for the update, with the clip coefficient read from device memory
+// (no host synchronisation, no separate grad *= coef pass).  The tensor table travels in the kernel parameters
+// (48 tensors per launch); a block owns one 4096-element chunk of one tensor.
+// HBM-bound: 4 B/param for the norm, 16 B read + 12 B written per param for the update.
+#include "../../include/b200_convlstm.h"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int MT_MAX = 48;
+constexpr int MT_CHUNK = 4096;  // elements per block: 256 threads x 4 float4
+
+struct MtTable {
+    float* p[MT_MAX];
+    float* g[MT_MAX];
+    float* m[MT_MAX];
+    float* v[MT_MAX];
+    long long n[MT_MAX];
+    int first_chunk[MT_MAX + 1];
+    int count;
+};
+
+struct AdamCfg {
+    float lr, beta1, beta2, eps, weight_decay;
+    float step_size;      // lr / (1 - beta1^t)
+    float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+    float max_norm;       // <= 0: no clipping
+};
+
+__device__ __forceinline__ int mt_locate(const MtTable& tb, int blk) {
+    int t = 0;
+    while (t + 1 < tb.count && blk >= tb.first_chunk[t + 1]) ++t;
+    return t;
+}
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__global__ void __launch_bounds__(256) grad_sqnorm_multi_kernel(const __grid_constant__ MtTable tb, double* __restrict__ out) {
+    const int t = mt_locate(tb, blockIdx.x);
+    const long long off = static_cast<long long>(blockIdx.x - tb.first_chunk[t]) * MT_CHUNK;
+    const long long rem = tb.n[t] - off;
+    const int len = rem < MT_CHUNK ? static_cast<int>(rem) : MT_CHUNK;
+    const float* g = tb.g[t] + off;
+    float s = 0.f;
+    if (len == MT_CHUNK && aligned16(g)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(g) + k * 256 + threadIdx.x);
+            s = fmaf(a.x, a.x, s), s = fmaf(a.y, a.y, s), s = fmaf(a.z, a.z, s), s = fmaf(a.w, a.w, s);
+        }
+    } else {
+        for (int i = threadIdx.x; i < len; i += 256) s = fmaf(g[i], g[i], s);
+    }
+    double d = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        atomicAdd(out, tot);
+    }
+}
+
+// torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+__device__ __forceinline__ float clip_coef(const double* sqnorm, float max_norm) {
+    if (!sqnorm || max_norm <= 0.f) return 1.f;
+    const float c = max_norm / (static_cast<float>(sqrt(*sqnorm)) + 1e-6f);
+    return c < 1.f ? c : 1.f;
+}
+
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamCfg& c, float clip) {
+    g *= clip;
+    p -= c.lr * c.weight_decay * p;
+    m += (g - m) * (1.f - c.beta1);                      // exp_avg.lerp_(grad, 1 - beta1)
+    v = c.beta2 * v + (1.f - c.beta2) * g * g;
+    const float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
+    p -= c.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ MtTable tb, const AdamCfg c,
+                                                          const double* __restrict__ sqnorm) {
+    const int t = mt_locate(tb, blockIdx.x);
+    const long long off = static_cast<long long>(blockIdx.x - tb.first_chunk[t]) * MT_CHUNK;
+    const long long rem = tb.n[t] - off;
+    const int len = rem < MT_CHUNK ? static_cast<int>(rem) : MT_CHUNK;
+    float* p = tb.p[t] + off;
+    const float* g = tb.g[t] + off;
+    float* m = tb.m[t] + off;
+    float* v = tb.v[t] + off;
+    const float clip = clip_coef(sqnorm, c.max_norm);
+    if (len == MT_CHUNK && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v)) {
+        float4 P[4], G[4], M[4], V[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // all loads before the first use
+            const int i = k * 256 + threadIdx.x;
+            P[k] = reinterpret_cast<const float4*>(p)[i];
+            G[k] = __ldg(reinterpret_cast<const float4*>(g) + i);
+            M[k] = reinterpret_cast<const float4*>(m)[i];
+            V[k] = reinterpret_cast<const float4*>(v)[i];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = k * 256 + threadIdx.x;
+            adamw_one(P[k].x, G[k].x, M[k].x, V[k].x, c, clip);
+            adamw_one(P[k].y, G[k].y, M[k].y, V[k].y, c, clip);
+            adamw_one(P[k].z, G[k].z, M[k].z, V[k].z, c, clip);
+            adamw_one(P[k].w, G[k].w, M[k].w, V[k].w, c, clip);
+            reinterpret_cast<float4*>(p)[i] = P[k];
+            reinterpret_cast<float4*>(m)[i] = M[k];
+            reinterpret_cast<float4*>(v)[i] = V[k];
+        }
+    } else {
+        for (int i = threadIdx.x; i < len; i += 256) {
+            float pp = p[i], mm = m[i], vv = v[i];
+            adamw_one(pp, g[i], mm, vv, c, clip);
+            p[i] = pp, m[i] = mm, v[i] = vv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) grad_scale_multi_kernel(const __grid_constant__ MtTable tb, const double* __restrict__ sqnorm,
+                                                               float max_norm) {
+    const float clip = clip_coef(sqnorm, max_norm);
+    if (clip == 1.f) return;
+    const int t = mt_locate(tb, blockIdx.x);
+    const long long off = static_cast<long long>(blockIdx.x - tb.first_chunk[t]) * MT_CHUNK;
+    const long long rem = tb.n[t] - off;
+    const int len = rem < MT_CHUNK ? static_cast<int>(rem) : MT_CHUNK;
+    float* g = tb.g[t] + off;
+    for (int i = threadIdx.x; i < len; i += 256) g[i] *= clip;
+}
+
+// Calls launch(table) for consecutive groups of <= MT_MAX non-empty tensors.
+template <class F>
+static int for_each_group(int n, float* const* p, float* const* g, float* const* m, float* const* v, const long long* numel,
+                          F&& launch) {
+    int i = 0;
+    while (i < n) {
+        MtTable tb;
+        tb.count = 0;
+        tb.first_chunk[0] = 0;
+        while (i < n && tb.count < MT_MAX) {
+            if (numel[i] > 0) {
+                const long long chunks = (numel[i] + MT_CHUNK - 1) / MT_CHUNK;
+                if (tb.first_chunk[tb.count] + chunks > 0x7fffffffLL) return B200_ERR_ARG;
+                const int k = tb.count++;
+                tb.p[k] = p ? p[i] : nullptr;
+                tb.g[k] = g[i];
+                tb.m[k] = m ? m[i] : nullptr;
+                tb.v[k] = v ? v[i] : nullptr;
+                tb.n[k] = numel[i];
+                tb.first_chunk[k + 1] = tb.first_chunk[k] + static_cast<int>(chunks);
+            }
+            ++i;
+        }
+        if (tb.count > 0) {
+            const int rc = launch(tb);
+            if (rc != B200_OK) return rc;
+        }
+    }
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_grad_sqnorm_multi(int n, const void* const* grads, const long long* numel, double* sqnorm, void* stream) {
+    if (n < 0 || (n > 0 && (!grads || !numel)) || !sqnorm) {
+        set_last_error("b200_grad_sqnorm_multi: bad arguments");
+        return B200_ERR_ARG;
+    }
+    for (int i = 0; i < n; ++i)
+        if (numel[i] < 0 || (numel[i] > 0 && !grads[i])) {
+            set_last_error("b200_grad_sqnorm_multi: tensor %d: null pointer or negative size", i);
+            return B200_ERR_ARG;
+        }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B200_CUDA_CHECK(cudaMemsetAsync(sqnorm, 0, sizeof(double), st));
+    return for_each_group(n, nullptr, reinterpret_cast<float* const*>(const_cast<void* const*>(grads)), nullptr, nullptr, numel,
+                          [&](const MtTable& tb) {
+                              grad_sqnorm_multi_kernel<<<tb.first_chunk[tb.count], 256, 0, st>>>(tb, sqnorm);
+                              B200_CUDA_CHECK(cudaGetLastError());
+                              return B200_OK;
+                          });
+}
+
+extern "C" int b200_grad_clip_multi(int n, void* const* grads, const long long* numel, const double* sqnorm, float max_norm,
+                                    void* stream) {
+    if (n < 0 || (n > 0 && (!grads || !numel)) || !sqnorm || !(max_norm > 0.f)) {
+        set_last_error("b200_grad_clip_multi: bad arguments");
+        return B200_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return for_each_group(n, nullptr, reinterpret_cast<float* const*>(grads), nullptr, nullptr, numel, [&](const MtTable& tb) {
+        grad_scale_multi_kernel<<<tb.first_chunk[tb.count], 256, 0, st>>>(tb, sqnorm, max_norm);
+        B200_CUDA_CHECK(cudaGetLastError());
+        return B200_OK;
+    });
+}
+
+extern "C" int b200_adamw_multi(int n, void* const* params, const void* const* grads, void* const* exp_avg,
+                                void* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, long long step, const double* sqnorm, float max_norm, void* stream) {
+    if (n < 0 || (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !numel)) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
+        !(beta2 >= 0.f && beta2 < 1.f)) {
+        set_last_error("b200_adamw_multi: bad arguments");
+        return B200_ERR_ARG;
+    }
+    for (int i = 0; i < n; ++i)
+        if (numel[i] < 0 || (numel[i] > 0 && (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]))) {
+            set_last_error("b200_adamw_multi: tensor %d: null pointer or negative size", i);
+            return B200_ERR_ARG;
+        }
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+    AdamCfg c{lr, beta1, beta2, eps, weight_decay, static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), max_norm};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return for_each_group(n, reinterpret_cast<float* const*>(params), reinterpret_cast<float* const*>(const_cast<void* const*>(grads)),
+                          reinterpret_cast<float* const*>(exp_avg), reinterpret_cast<float* const*>(exp_avg_sq), numel,
+                          [&](const MtTable& tb) {
+                              adamw_multi_kernel<<<tb.first_chunk[tb.count], 256, 0, st>>>(tb, c, sqnorm);
+                              B200_CUDA_CHECK(cudaGetLastError());
+                              return B200_OK;
+                          });
+}
