@@ -299,7 +299,14 @@ def run_b200_arm(args, out):
         torch.cuda.synchronize()
         ev, _lib.TIMER = _lib.TIMER, None
         agg = {}
-        for label, a, b, work in ev:
+        if args.timeline:
+            # start / end of every C-ABI call relative to the start of the step, with the stream it ran on
+            streams = {}
+            with open(args.timeline, "w") as tf:
+                tf.write("start_ms,end_ms,stream,label\n")
+                for label, a, b, work, st in ev:
+                    tf.write(f"{e0.elapsed_time(a):.4f},{e0.elapsed_time(b):.4f},{streams.setdefault(st, len(streams))},{label}\n")
+        for label, a, b, work, _st in ev:
             d = agg.setdefault(label, [0, 0.0, 0.0, 0.0])
             d[0] += 1
             d[1] += a.elapsed_time(b)
@@ -451,6 +458,7 @@ def main():
                     help="1: replay the step from a CUDA graph (single GPU).  Measured on B200: 232.7 ms graphed vs "
                          "233.3 ms eager -- the step is GPU-bound, the host runs ahead -- so the default is eager")
     ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
+    ap.add_argument("--timeline", default="", help="with --breakdown: write start/end/stream of every C-ABI call to this CSV")
     ap.add_argument("--profile-steps", type=int, default=0, help="run 1 warm-up + N untimed steps and exit (for ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -887,3 +887,66 @@ def test_multi_tensor_clip_adamw_matches_torch(n_tensors, clip):
     o_fused.step()
     for a, b in zip(fused, after_t):
         assert np.abs(_np(a) - _np(b)).max() <= 2e-6 * max(1.0, float(b.abs().max()))
+
+
+def _bg_grads(model, x, dy, background, twice=False, keep_grads=False):
+    """Gradients of sum(y * dy) with the weight gradients in line or on the background stream (every background
+    block delayed by ~10 ms, so that anything reading a gradient too early sees memory that is not written yet)."""
+    from unet_convlstm_b200 import ops
+    old = (ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY)
+    ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY = background, (20_000_000 if background else 0)
+    try:
+        if not keep_grads:
+            model.zero_grad(set_to_none=True)
+        poison = torch.full((256 << 20,), float("nan"), device="cuda")   # freed memory is NaN
+        del poison
+        n0 = ops.BG_BLOCKS[0]
+        if twice:
+            k = x.shape[1] // 2
+            out1, st = model(x[:, :k])
+            out2, _ = model(x[:, k:], st)
+            y = torch.stack(list(out1) + list(out2), dim=1)
+        else:
+            out, _ = model(x)
+            y = torch.stack(out, dim=1)
+        (y * dy).sum().backward()
+        used = ops.BG_BLOCKS[0] - n0
+        return {k: p.grad.detach().clone() for k, p in model.named_parameters()}, used
+    finally:
+        ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY = old
+
+
+def test_background_wgrad_stream_matches_inline():
+    """Weight gradients produced on the background stream (ops.background) against the single-stream backward:
+    a plain step, a step whose parameters are used TWICE in one graph (state carried between two calls: autograd sums
+    the two contributions on the current stream, so the blocks must fall back in line), and gradient accumulation
+    into existing .grad tensors (also in line)."""
+    import unet_convlstm_b200 as pkg
+    from train.unet import TemporalUNetDualView
+    pkg.set_precision("fp32")
+    try:
+        torch.manual_seed(4)
+        m = TemporalUNetDualView(base_ch=4, use_skip_lstm=True).cuda()
+        g = torch.Generator(device="cuda").manual_seed(1)
+        x = torch.rand(2, 4, 2, 32, 32, device="cuda", generator=g) * 2
+        dy = torch.randn(2, 4, 1, 32, 32, device="cuda", generator=g)
+        ref, used = _bg_grads(m, x, dy, False)
+        assert used == 0
+        got, used = _bg_grads(m, x, dy, True)
+        assert used >= 20, used                                   # 18 conv + 4 convT + 3 LSTM layers
+        for k in ref:
+            assert torch.isfinite(got[k]).all(), k
+            assert rel2(_np(got[k]), _np(ref[k])) < 1e-4, k
+        ref2, _ = _bg_grads(m, x, dy, False, twice=True)
+        got2, used = _bg_grads(m, x, dy, True, twice=True)
+        assert used == 0, used                                    # every parameter has two uses: all in line
+        for k in ref2:
+            assert rel2(_np(got2[k]), _np(ref2[k])) < 1e-4, k
+        got3, used = _bg_grads(m, x, dy, True, keep_grads=True)   # accumulates on top of got2's .grad tensors
+        assert used == 0, used
+        for k in ref:
+            assert rel2(_np(got3[k]), _np(ref2[k] + ref[k])) < 1e-4, k
+        _, used = _bg_grads(m, x, dy, True)                       # and the background path is taken again afterwards
+        assert used >= 20, used
+    finally:
+        pkg.set_precision("bf16")

@@ -102,7 +102,7 @@ def call(name: str, *args, tag: str = "", work=None):
     if timer is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        timer.append((name + (" " + tag if tag else ""), e0, e1, work))
+        timer.append((name + (" " + tag if tag else ""), e0, e1, work, torch.cuda.current_stream().cuda_stream))
     CALLS[name] = CALLS.get(name, 0) + 1
     if rc != 0:
         raise RuntimeError(f"{name} failed: rc={rc}: {last_error()}")

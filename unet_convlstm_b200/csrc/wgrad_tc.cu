@@ -420,6 +420,11 @@ static int launch_wgrad_impl(const CUtensorMap& tz, const CUtensorMap& ts, const
     if (!attr_set) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES));
+        // the whole unified L1/shared array as shared memory: the kernel itself only needs its ring, but the
+        // remainder lets HBM-bound blocks of another stream (BatchNorm sums: 9 KB static) share the SM when the
+        // weight gradient runs on the background stream (with the default carve-out the next step is 196 KB)
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     int total = p.out_tiles * p.splits;

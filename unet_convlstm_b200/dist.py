@@ -12,6 +12,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 class GradReducer:
     def __init__(self, params, bucket_bytes: int = 64 << 20, process_group=None):
@@ -32,6 +34,8 @@ class GradReducer:
         self._pending = [0] * len(self.buckets)
         self._works = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        for p in self.params:
+            p._b200_bg_aware = True  # _on_grad orders its reads after the background stream (ops.background)
         self.reset()
 
     def _add_bucket(self, plist):
@@ -49,6 +53,18 @@ class GradReducer:
         self._works = []
 
     def _on_grad(self, p):
+        if p.is_cuda and ops.WGRAD_STREAM:
+            # Weight gradients may still be in flight on the background stream (ops.background).  The bucket copy and
+            # the all-reduce are queued THERE -- after the gradient's producer, and after the current stream for the
+            # gradients made on it -- so the current stream never waits for a weight gradient during backward.
+            cur, side = torch.cuda.current_stream(), ops.background_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._bucket_grad(p, side)
+            return
+        self._bucket_grad(p, None)
+
+    def _bucket_grad(self, p, side):
         b = self._bucket_of[p]
         flat, entries = self.buckets[b]
         for q, off, n in entries:
@@ -56,6 +72,8 @@ class GradReducer:
                 view = flat[off:off + n].view_as(p)
                 if p.grad.data_ptr() != view.data_ptr():
                     view.copy_(p.grad)
+                    if side is not None:
+                        p.grad.record_stream(side)
                     p.grad = view  # the gradient lives in the bucket from now on
                 break
         self._pending[b] -= 1
@@ -64,6 +82,8 @@ class GradReducer:
 
     def finish(self):
         """Waits for the outstanding all-reduces and turns sums into means.  Call after backward."""
+        if ops.WGRAD_STREAM and self.params and self.params[0].is_cuda:
+            ops.background_join()
         for w in self._works:
             w.wait()
         if self.world > 1:
@@ -75,3 +95,5 @@ class GradReducer:
     def remove(self):
         for h in self._hooks:
             h.remove()
+        for p in self.params:
+            p._b200_bg_aware = False

@@ -17,6 +17,23 @@ class WeightCache:
 
     def __init__(self):
         self._d = {}
+        self._open = 0        # forward passes (with a graph) whose backward has not run yet
+        self._shared = False  # the parameters were used more than once in the graph(s) still open
+
+    def note_forward(self):
+        self._open += 1
+        if self._open > 1:
+            self._shared = True
+
+    def note_backward(self) -> bool:
+        """True if this backward is the ONLY gradient contribution the parameters receive in this pass (autograd sums
+        several contributions on the current stream, which rules out producing one of them on the background
+        stream, ops.background)."""
+        single = not self._shared
+        self._open = max(0, self._open - 1)
+        if self._open == 0:
+            self._shared = False
+        return single
 
     def get(self, key, params, builder):
         ver = tuple((p.data_ptr(), p._version) for p in params if p is not None)
@@ -33,6 +50,14 @@ class WeightCache:
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+def _count_use(ctx, cache) -> bool:
+    """Registers a forward pass that will be differentiated (see WeightCache.note_backward)."""
+    if any(ctx.needs_input_grad):
+        cache.note_forward()
+        return True
+    return False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,6 +118,7 @@ class ConvBnRelu(torch.autograd.Function):
             ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
             ctx.tstride = stats[4]
             ctx.training, ctx.cache, ctx.has_bias, ctx.first = training, cache, bias is not None, True
+            ctx.counted = _count_use(ctx, cache)
             return y
         ctx.first = False
         wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
@@ -107,11 +133,13 @@ class ConvBnRelu(torch.autograd.Function):
         ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
         ctx.tstride = stats[4]
         ctx.training, ctx.cache, ctx.has_bias = training, cache, bias is not None
+        ctx.counted = _count_use(ctx, cache)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x0, x1, z, weight, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        single = ctx.cache.note_backward() if ctx.counted else True
         dt = z.dtype
         dy = _c(dy)
         if dy.dtype != dt:
@@ -124,23 +152,34 @@ class ConvBnRelu(torch.autograd.Function):
         dz, dgamma, dbeta, dbias = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
                                                    ctx.has_bias)
         # weight gradient, batched over all T*B images
-        if ctx.first:
-            dweight = ops.conv_first_wgrad(dz, x0, K)
-        else:
+        def wgrad():
+            if ctx.first:
+                return ops.conv_first_wgrad(dz, x0, K)
             dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
             ops.conv_wgrad(dz, x0, ks, dwp, 0)
             if x1 is not None:
                 ops.conv_wgrad(dz, x1, ks, dwp, C0)
-            dweight = ops.unpack_conv_wgrad(dwp, K)
-        # data gradient, split over the two sources of the virtual concat
-        dx0 = dx1 = None
-        need0, need1 = ctx.needs_input_grad[0], (x1 is not None and ctx.needs_input_grad[1])
-        if need0 or need1:
+            return ops.unpack_conv_wgrad(dwp, K)
+
+        def dgrad():
+            # data gradient, split over the two sources of the virtual concat
             wd = ctx.cache.get(("dgrad", dt, C0 + C1), (weight,),
                                lambda: _dgrad_pack_padded(weight, dt, C0 + C1))
-            dx0 = torch.empty_like(x0)
-            dx1 = torch.empty_like(x1) if x1 is not None else None
-            ops.conv_fwd(dz, None, wd, None, ks, dx0, dx1)
+            d0 = torch.empty_like(x0)
+            d1 = torch.empty_like(x1) if x1 is not None else None
+            ops.conv_fwd(dz, None, wd, None, ks, d0, d1)
+            return d0, d1
+
+        dx0 = dx1 = None
+        need0, need1 = ctx.needs_input_grad[0], (x1 is not None and ctx.needs_input_grad[1])
+        bg = ops.background(weight, dz, x0, x1, allow=single)
+        if bg.active and (need0 or need1):
+            dx0, dx1 = dgrad()     # the critical path first: the background wgrad takes the SMs the dgrad frees
+        with bg:
+            dweight = wgrad()
+            bg.keep(dweight)
+        if not bg.active and (need0 or need1):
+            dx0, dx1 = dgrad()
         return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -214,26 +253,30 @@ class ConvT2x2(torch.autograd.Function):
         wf, _ = cache.get(("convT", dt), (weight,), lambda: ops.pack_convT_weight(weight, dt))
         y = ops.convT2x2_fwd(x, wf, bias.detach() if bias is not None else None, Cout, Hd, Wd)
         ctx.save_for_backward(x, weight)
-        ctx.cache, ctx.has_bias = cache, bias is not None
+        ctx.cache, ctx.has_bias, ctx.bias = cache, bias is not None, bias
+        ctx.counted = _count_use(ctx, cache)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
+        single = ctx.cache.note_backward() if ctx.counted else True
         dt = x.dtype
         T, B, H, W, Cin = x.shape
         Cout = weight.shape[1]
         du = ops.unshuffle2x2(_c(dy).to(dt), H, W)  # [T,B,H,W,4*Cout]
-        dbias = ops.colsum(T * B * H * W * 4, du, Cout) if ctx.has_bias else None
-        dwp = torch.zeros((1, 4 * Cout, Cin), device=x.device, dtype=torch.float32)
-        ops.conv_wgrad(du, x, 1, dwp, 0)
-        dweight = torch.empty_like(weight)
-        ops.copy_(dweight.view(Cin, Cout, 4), dwp.view(4, Cout, Cin).permute(2, 1, 0))
         dx = None
         if ctx.needs_input_grad[0]:
             _, wb = ctx.cache.get(("convT", dt), (weight,), lambda: ops.pack_convT_weight(weight, dt))
             dx = torch.empty_like(x)
             ops.conv_fwd(du, None, wb, None, 1, dx)
+        with ops.background((weight, ctx.bias), du, x, allow=single) as bg:
+            dbias = ops.colsum(T * B * H * W * 4, du, Cout) if ctx.has_bias else None
+            dwp = torch.zeros((1, 4 * Cout, Cin), device=x.device, dtype=torch.float32)
+            ops.conv_wgrad(du, x, 1, dwp, 0)
+            dweight = torch.empty_like(weight)
+            ops.copy_(dweight.view(Cin, Cout, 4), dwp.view(4, Cout, Cin).permute(2, 1, 0))
+            bg.keep(dweight, dbias)
         return dx, dweight, dbias, None, None, None
 
 
@@ -311,7 +354,8 @@ class ConvLSTMSeq(torch.autograd.Function):
                                           c_all[t + 1], h_all[t + 1], gates[t], ks, zbuf)
         ctx.save_for_backward(x_seq, weight)
         ctx.h_all, ctx.c_all, ctx.gates = h_all, c_all, gates
-        ctx.have_h0, ctx.cache, ctx.has_bias = have_h0, cache, bias is not None
+        ctx.have_h0, ctx.cache, ctx.has_bias, ctx.bias = have_h0, cache, bias is not None, bias
+        ctx.counted = _count_use(ctx, cache)
         h_seq = h_all[1:]
         c_T = c_all[T]
         ctx.mark_non_differentiable()
@@ -375,13 +419,16 @@ class ConvLSTMSeq(torch.autograd.Function):
         T, B, H, W, Cin = x_seq.shape
         Ch = weight.shape[0] // 4
         ks = weight.shape[2]
-        dwp = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=x_seq.device, dtype=torch.float32)
-        ops.conv_wgrad(dz_all, x_seq, ks, dwp, 0)
-        if ctx.have_h0:
-            ops.conv_wgrad(dz_all, h_all[:T], ks, dwp, Cin)
-        elif T > 1:
-            ops.conv_wgrad(dz_all[1:], h_all[1:T], ks, dwp, Cin)  # h_{-1} = 0 contributes nothing
-        dweight = ops.unpack_conv_wgrad(dwp, Cin + Ch)
-        dbias = ops.colsum(T * B * H * W, dz_all, 4 * Ch) if ctx.has_bias else None
+        single = ctx.cache.note_backward() if ctx.counted else True
+        with ops.background((weight, ctx.bias), dz_all, x_seq, h_all, allow=single) as bg:
+            dwp = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=x_seq.device, dtype=torch.float32)
+            ops.conv_wgrad(dz_all, x_seq, ks, dwp, 0)
+            if ctx.have_h0:
+                ops.conv_wgrad(dz_all, h_all[:T], ks, dwp, Cin)
+            elif T > 1:
+                ops.conv_wgrad(dz_all[1:], h_all[1:T], ks, dwp, Cin)  # h_{-1} = 0 contributes nothing
+            dweight = ops.unpack_conv_wgrad(dwp, Cin + Ch)
+            dbias = ops.colsum(T * B * H * W, dz_all, 4 * Ch) if ctx.has_bias else None
+            bg.keep(dweight, dbias)
         ctx.h_all = ctx.c_all = ctx.gates = None
         return dx_seq, dh0, dc0, dweight, dbias, None

@@ -32,6 +32,7 @@ class GraphedTrainStep:
         self.y = y.clone()
         self.with_optimizer = with_optimizer
         saved = (ops.CELL_TIMER, _lib.TIMER)
+        saved_bg, ops.WGRAD_STREAM = ops.WGRAD_STREAM, False  # one stream inside the capture
         ops.CELL_TIMER, _lib.TIMER = None, None  # CUDA events cannot be timed inside a capture
         try:
             side = torch.cuda.Stream()
@@ -47,6 +48,7 @@ class GraphedTrainStep:
                 self.loss = self._eager_step(zero=False)
         finally:
             ops.CELL_TIMER, _lib.TIMER = saved
+            ops.WGRAD_STREAM = saved_bg
         if _lib.lib().b200_device_error() != 0:
             raise RuntimeError("device watchdog flag set during graph capture")
 

@@ -467,6 +467,101 @@ PERSISTENT_LSTM = os.environ.get("B200_PERSISTENT_LSTM", "1") != "0"
 # of the epilogue competes with the L2-bound main loop and the per-step pair of launches is 0-13 % faster.
 FUSED_BPTT = os.environ.get("B200_FUSED_BPTT", "0") == "1"
 
+# Weight gradients on a background stream (1) or in line on the current stream (0).  A weight gradient is a leaf of
+# backward: nothing downstream waits for it, while the HBM-bound kernels of the NEXT layer's backward (BatchNorm
+# sums / apply, gate gradients, pooling) leave the tensor pipes idle.  With the wgrad kernels queued on a second
+# stream their CTAs share the SMs with those pointwise blocks (a persistent wgrad CTA leaves ~40 K registers and room
+# for two 256-thread blocks per SM).  The current stream re-joins the background stream when backward ends.
+WGRAD_STREAM = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
+_BG_DEBUG_DELAY = int(os.environ.get("B200_WGRAD_STREAM_DEBUG_DELAY", "0"))  # spin cycles before every background block (tests)
+BG_BLOCKS = [0]  # blocks that actually ran on the background stream (tests)
+_bg_streams: dict = {}
+_bg_joined_task = [-1]
+
+
+def background_stream(device=None):
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    st = _bg_streams.get(idx)
+    if st is None:
+        st = _bg_streams[idx] = torch.cuda.Stream(idx)
+    return st
+
+
+def background_join():
+    """The current stream waits for everything queued on the background stream so far."""
+    st = _bg_streams.get(torch.cuda.current_device())
+    if st is not None:
+        torch.cuda.current_stream().wait_stream(st)
+
+
+def _leaf_takes_gradient_as_is(p) -> bool:
+    """True if autograd will only STORE the new gradient of leaf `p` (no kernel on the current stream reads it during
+    backward): .grad is still empty and nobody hooked the tensor -- except hooks that declare themselves aware of the
+    background stream (dist.GradReducer sets `_b200_bg_aware`)."""
+    if p.grad is not None or not p.is_leaf:
+        return False
+    if getattr(p, "_backward_hooks", None):
+        return False
+    if getattr(p, "_post_accumulate_grad_hooks", None) and not getattr(p, "_b200_bg_aware", False):
+        return False
+    return True
+
+
+class background:
+    """`with background(params, *inputs) as bg:` (params: the leaf or leaves whose gradients the block produces) -- the
+    launches inside run on the background stream, ordered
+    after everything already queued on the current stream; `inputs` are tensors the block reads (kept away from the
+    caching allocator until the background work is done).  Falls back to the current stream (bg.active False) outside
+    a backward pass, when the switch is off, when `allow` is False (the caller knows of a second gradient contribution
+    to the same parameters), or when autograd would touch the new gradient during backward (_leaf_takes_gradient_as_is)."""
+
+    def __init__(self, grad_target, *inputs, allow=True):
+        self.inputs = [t for t in inputs if t is not None]
+        task = torch._C._current_graph_task_id()
+        self.active = bool(WGRAD_STREAM and allow and task != -1 and not torch.is_grad_enabled()
+                           and all(_leaf_takes_gradient_as_is(p) for p in
+                                   (grad_target if isinstance(grad_target, (tuple, list)) else (grad_target,))
+                                   if p is not None))
+        self.task = task
+
+    def __enter__(self):
+        if not self.active:
+            return self
+        cur = torch.cuda.current_stream()
+        self.side = background_stream()
+        self.side.wait_stream(cur)
+        for t in self.inputs:
+            t.record_stream(self.side)
+        if _bg_joined_task[0] != self.task:
+            # one join per backward pass: whoever reads the gradients after backward() sees them complete
+            _bg_joined_task[0] = self.task
+            torch.autograd.Variable._execution_engine.queue_callback(_end_of_backward_join)
+        BG_BLOCKS[0] += 1
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        if _BG_DEBUG_DELAY:
+            torch.cuda._sleep(_BG_DEBUG_DELAY)
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def keep(self, *tensors):
+        """Tensors created inside the block that the CURRENT stream will own afterwards (returned gradients)."""
+        if self.active:
+            cur = torch.cuda.current_stream()
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(cur)
+
+
+def _end_of_backward_join():
+    _bg_joined_task[0] = -1
+    background_join()
+
+
 # bench.py sets this to a list to time every fused cell launch with CUDA events on the launching stream:
 # entries are (start_event, end_event, algorithmic_flops)
 CELL_TIMER = None
