@@ -893,8 +893,9 @@ def _bg_grads(model, x, dy, background, twice=False, keep_grads=False):
     """Gradients of sum(y * dy) with the weight gradients in line or on the background stream (every background
     block delayed by ~10 ms, so that anything reading a gradient too early sees memory that is not written yet)."""
     from unet_convlstm_b200 import ops
-    old = (ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY)
+    old = (ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY, ops.LSTM_WGRAD_CHUNK)
     ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY = background, (20_000_000 if background else 0)
+    ops.LSTM_WGRAD_CHUNK = 2       # T = 4: one chunk [2, 4) queued during the BPTT sweep, [0, 2) after it
     try:
         if not keep_grads:
             model.zero_grad(set_to_none=True)
@@ -911,9 +912,9 @@ def _bg_grads(model, x, dy, background, twice=False, keep_grads=False):
             y = torch.stack(out, dim=1)
         (y * dy).sum().backward()
         used = ops.BG_BLOCKS[0] - n0
-        return {k: p.grad.detach().clone() for k, p in model.named_parameters()}, used
+        return {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in model.named_parameters()}, used
     finally:
-        ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY = old
+        ops.WGRAD_STREAM, ops._BG_DEBUG_DELAY, ops.LSTM_WGRAD_CHUNK = old
 
 
 def test_background_wgrad_stream_matches_inline():
@@ -948,5 +949,15 @@ def test_background_wgrad_stream_matches_inline():
             assert rel2(_np(got3[k]), _np(ref2[k] + ref[k])) < 1e-4, k
         _, used = _bg_grads(m, x, dy, True)                       # and the background path is taken again afterwards
         assert used >= 20, used
+        frozen = [k for k, p in m.named_parameters() if k.startswith("down1") and k.endswith(".0.weight")]
+        assert frozen
+        for k, p in m.named_parameters():
+            p.requires_grad_(k not in frozen)                     # frozen conv weights: no weight-gradient GEMM
+        got4, _ = _bg_grads(m, x, dy, True)
+        for k in ref:
+            if k in frozen:
+                assert got4[k] is None
+            else:
+                assert rel2(_np(got4[k]), _np(ref[k])) < 1e-4, k
     finally:
         pkg.set_precision("bf16")

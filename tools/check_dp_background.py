@@ -29,6 +29,7 @@ res = {}
 for mode in (False, True, True):
     ops.WGRAD_STREAM = mode
     ops._BG_DEBUG_DELAY = 30_000_000 if mode else 0
+    ops.LSTM_WGRAD_CHUNK = 2
     model.zero_grad(set_to_none=True)
     out, _ = model(x)
     compute_loss(torch.stack(out, dim=1), y, m).backward()

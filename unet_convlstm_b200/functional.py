@@ -172,12 +172,14 @@ class ConvBnRelu(torch.autograd.Function):
 
         dx0 = dx1 = None
         need0, need1 = ctx.needs_input_grad[0], (x1 is not None and ctx.needs_input_grad[1])
-        bg = ops.background(weight, dz, x0, x1, allow=single)
+        bg = ops.background(weight, dz, x0, x1, allow=single and ctx.needs_input_grad[2])
         if bg.active and (need0 or need1):
             dx0, dx1 = dgrad()     # the critical path first: the background wgrad takes the SMs the dgrad frees
-        with bg:
-            dweight = wgrad()
-            bg.keep(dweight)
+        dweight = None
+        if ctx.needs_input_grad[2]:          # frozen weights (fine-tuning a decoder): no weight-gradient GEMM
+            with bg:
+                dweight = wgrad()
+                bg.keep(dweight)
         if not bg.active and (need0 or need1):
             dx0, dx1 = dgrad()
         return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
@@ -391,6 +393,13 @@ class ConvLSTMSeq(torch.autograd.Function):
         dh_rec = [torch.empty((B, H, W, Ch), device=dev, dtype=dt) for _ in range(2)]
         dc_buf = [torch.empty((B, H, W, Ch), device=dev, dtype=torch.float32) for _ in range(2)]
         dh_b = None
+        # Weight gradient in chunks of timesteps on the background stream WHILE the sweep continues: the HBM-bound
+        # gate-gradient kernel of every step leaves the tensor pipes idle, and the chunk already swept fills them.
+        single = ctx.cache.note_backward() if ctx.counted else True
+        chunk = ops.LSTM_WGRAD_CHUNK
+        chunked = None
+        if chunk > 0 and T > chunk and ops.background((weight, ctx.bias), allow=single).active:
+            chunked = {"dwp": torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=dev, dtype=torch.float32), "hi": T}
         for t in reversed(range(T)):
             zero_prev = (t == 0 and not ctx.have_h0)
             ops.lstm_gates_bwd(gates[t], None if zero_prev else c_all[t], c_all[t + 1],
@@ -405,28 +414,46 @@ class ConvLSTMSeq(torch.autograd.Function):
                 # only the x columns of the data gradient are needed at t = 0 with a zero initial state
                 ops.conv_fwd(dz_all[t].unsqueeze(0), None, wd[:, :Cin, :].contiguous(), None, ks,
                              dx_seq[t].unsqueeze(0))
+            if chunked is not None and t > 0 and (T - t) % chunk == 0:
+                with ops.background((weight, ctx.bias), dz_all, x_seq, h_all, chunked["dwp"], allow=single):
+                    ConvLSTMSeq._wgrad_range(ctx, x_seq, h_all, dz_all, chunked["dwp"], t, chunked["hi"], Cin, ks)
+                chunked["hi"] = t
         dh0 = dc0 = None
         if ctx.have_h0:
             if ctx.needs_input_grad[1]:
                 dh0 = dh_b
             if ctx.needs_input_grad[2]:
                 dc0 = dc_next
-        return ConvLSTMSeq._finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0)
+        return ConvLSTMSeq._finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0, single, chunked)
 
     @staticmethod
-    def _finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0):
-        """Weight / bias gradients: one reduction over the whole sequence (K = T*B*H*W)."""
+    def _wgrad_range(ctx, x_seq, h_all, dz_all, dwp, lo, hi, Cin, ks):
+        """dwp += the weight gradient of timesteps [lo, hi): the x columns from x_t, the h columns from h_{t-1} =
+        h_all[t] (h_{-1} = 0 contributes nothing when the initial state is zero)."""
+        ops.conv_wgrad(dz_all[lo:hi], x_seq[lo:hi], ks, dwp, 0)
+        lo_h = lo if ctx.have_h0 else max(lo, 1)
+        if hi > lo_h:
+            ops.conv_wgrad(dz_all[lo_h:hi], h_all[lo_h:hi], ks, dwp, Cin)
+
+    @staticmethod
+    def _finish_backward(ctx, x_seq, weight, h_all, dz_all, dx_seq, dh0, dc0, single=None, chunked=None):
+        """Weight / bias gradients: one reduction over the whole sequence (K = T*B*H*W), or what is left of it when
+        the sweep already queued chunks."""
         T, B, H, W, Cin = x_seq.shape
         Ch = weight.shape[0] // 4
         ks = weight.shape[2]
-        single = ctx.cache.note_backward() if ctx.counted else True
-        with ops.background((weight, ctx.bias), dz_all, x_seq, h_all, allow=single) as bg:
-            dwp = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=x_seq.device, dtype=torch.float32)
-            ops.conv_wgrad(dz_all, x_seq, ks, dwp, 0)
-            if ctx.have_h0:
-                ops.conv_wgrad(dz_all, h_all[:T], ks, dwp, Cin)
-            elif T > 1:
-                ops.conv_wgrad(dz_all[1:], h_all[1:T], ks, dwp, Cin)  # h_{-1} = 0 contributes nothing
+        if single is None:
+            single = ctx.cache.note_backward() if ctx.counted else True
+        bg = ops.background((weight, ctx.bias), dz_all, x_seq, h_all, None if chunked is None else chunked["dwp"],
+                            allow=single)
+        if chunked is not None and not bg.active:
+            ops.background_join()  # chunks are in flight on the background stream; the rest runs in line
+        with bg:
+            if chunked is not None:
+                dwp, hi = chunked["dwp"], chunked["hi"]
+            else:
+                dwp, hi = torch.zeros((ks * ks, 4 * Ch, Cin + Ch), device=x_seq.device, dtype=torch.float32), T
+            ConvLSTMSeq._wgrad_range(ctx, x_seq, h_all, dz_all, dwp, 0, hi, Cin, ks)
             dweight = ops.unpack_conv_wgrad(dwp, Cin + Ch)
             dbias = ops.colsum(T * B * H * W, dz_all, 4 * Ch) if ctx.has_bias else None
             bg.keep(dweight, dbias)

@@ -474,6 +474,11 @@ FUSED_BPTT = os.environ.get("B200_FUSED_BPTT", "0") == "1"
 # for two 256-thread blocks per SM).  The current stream re-joins the background stream when backward ends.
 WGRAD_STREAM = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
 _BG_DEBUG_DELAY = int(os.environ.get("B200_WGRAD_STREAM_DEBUG_DELAY", "0"))  # spin cycles before every background block (tests)
+# ConvLSTM BPTT: timesteps per weight-gradient chunk queued on the background stream while the sweep continues
+# (0 = one weight-gradient reduction after the sweep, the default).  Measured (profiles/r01_background_wgrad_ab.txt):
+# chunks of 5 steps 207.6-208.5 ms against 206.8-206.9 ms per step, 4 or 10 steps ~212 ms -- the chunk's persistent
+# CTAs hold SMs the recurrent (critical-path) dgrad step of the main stream is waiting for.
+LSTM_WGRAD_CHUNK = int(os.environ.get("B200_LSTM_WGRAD_CHUNK", "0"))
 BG_BLOCKS = [0]  # blocks that actually ran on the background stream (tests)
 _bg_streams: dict = {}
 _bg_joined_task = [-1]
