@@ -192,6 +192,19 @@ int b200_shuffle2x2(const void* src, void* dst, const float* bias, long long IMG
 int b200_strided_copy(const void* src, int src_fp32, void* dst, int dst_fp32, const long long* dims,
                       const long long* src_strides, const long long* dst_strides, int accumulate, void* stream);
 
+/* Weight layout changes, once per weight and optimizer step.  src: the reference's parameter layout, fp32
+ * [A][B][taps] with the tap index fastest (Conv2d OIHW: A = Cout, B = Cin; ConvTranspose2d IOHW: A = Cin, B = Cout).
+ * b200_pack_weight writes the GEMM operand dst (bf16, or fp32 if dst_fp32):
+ *     a_contig = 0:  dst[tap' * tap_pitch + pa(a) * row_pitch + b]      (K-major B operand of the forward conv)
+ *     a_contig = 1:  dst[tap' * tap_pitch + b * row_pitch + pa(a)]      (data-gradient weights)
+ * tap' = taps-1-tap if flip else tap; pa = the gate interleave of the fused ConvLSTM kernel when perm_ch = Ch != 0
+ * (row g*Ch + nt*cht + j -> (nt*4 + g)*cht + j, unet.py:19,29 rows blocked i,f,g,o), identity otherwise.  Padding
+ * rows / columns of dst are the caller's (zero-filled beforehand).
+ * b200_unpack_wgrad is the way back for weight gradients: packed fp32 [taps][A][ldb] -> dst fp32 [A][B][taps]. */
+int b200_pack_weight(const float* src, int A, int B, int taps, void* dst, int dst_fp32, int a_contig, int flip,
+                     long long tap_pitch, long long row_pitch, int perm_ch, int perm_cht, void* stream);
+int b200_unpack_wgrad(const float* packed, int A, int B, int taps, long long ldb, float* dst, void* stream);
+
 /* The reference's training loss `compute_loss` (main.py:28-72): weighted L1 (weight 1 + 4|y|^3) + 0.005 x the
  * spatial-gradient loss on the [H-1, W-1] crop; with a mask (float 0/1, same shape) the means are masked and
  * carry the 1e-8 epsilon of main.py:42,65, with mask == NULL they are plain means (main.py:45,67).

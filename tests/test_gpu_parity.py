@@ -961,3 +961,84 @@ def test_background_wgrad_stream_matches_inline():
                 assert rel2(_np(got4[k]), _np(ref[k])) < 1e-4, k
     finally:
         pkg.set_precision("bf16")
+
+
+@pytest.mark.parametrize("which", ["torch_fused", "torch_foreach", "b200"])
+def test_packed_weights_follow_the_optimizer(which):
+    """The packed bf16 weight copies must be rebuilt after EVERY optimizer step -- including torch's fused
+    optimizers, whose `torch._fused_adamw_` updates the parameters without touching their version counter, and this
+    package's AdamW, which writes through raw pointers.  A model trained for two steps must answer exactly like a
+    fresh model (empty caches) loaded with its state_dict: in eval mode (folded BatchNorm), and in train mode."""
+    import copy
+    import unet_convlstm_b200 as pkg
+    from train.unet import TemporalUNetDualView
+    from unet_convlstm_b200 import optim
+    pkg.set_precision("bf16")
+    torch.manual_seed(8)
+    m = TemporalUNetDualView(base_ch=16, use_skip_lstm=True).cuda()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand(2, 3, 2, 32, 32, device="cuda", generator=g) * 2
+    dy = torch.randn(2, 3, 1, 32, 32, device="cuda", generator=g)
+    if which == "b200":
+        opt = optim.AdamW(m.parameters(), lr=3e-2)
+    else:
+        opt = torch.optim.AdamW(m.parameters(), lr=3e-2, fused=(which == "torch_fused"),
+                                foreach=(which == "torch_foreach"))
+    m.train()
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        out, _ = m(x)
+        (torch.stack(out, dim=1) * dy).sum().backward()
+        opt.step()
+    fresh = TemporalUNetDualView(base_ch=16, use_skip_lstm=True).cuda()
+    fresh.load_state_dict(copy.deepcopy(m.state_dict()))
+    m.eval(), fresh.eval()
+    with torch.no_grad():
+        a = torch.stack(m(x)[0], dim=1)
+        b = torch.stack(fresh(x)[0], dim=1)
+    assert torch.equal(a, b), float((a - b).abs().max())
+    m.train(), fresh.train()
+    a = torch.stack(m(x)[0], dim=1)
+    b = torch.stack(fresh(x)[0], dim=1)
+    assert torch.equal(a, b), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("N,K,ks,kpad", [(64, 64, 3, None), (40, 18, 3, 32), (128, 2, 3, 16), (96, 200, 1, None),
+                                         (4096, 2048, 3, None)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_weight_pack_kernels_exact(N, K, ks, kpad, dtype):
+    """b200_pack_weight / b200_unpack_wgrad (tiled through shared memory) against the index formulas they
+    implement, written with torch views: pure data movement (+ one bf16 rounding), so bit-exact.  Ragged tiles
+    (A, B not multiples of 32), zero-padded K, 1x1 and 3x3 taps, and the 75 M-parameter cell weight."""
+    from unet_convlstm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    w = torch.randn(N, K, ks, ks, device="cuda", generator=g)
+    taps, Kp = ks * ks, (K if kpad is None else kpad)
+    wt = w.reshape(N, K, taps)
+    ref = torch.zeros(taps, N, Kp, device="cuda", dtype=dtype)
+    ref[:, :, :K] = wt.permute(2, 0, 1).to(dtype)
+    assert torch.equal(ops.pack_conv_weight(w, dtype, kpad), ref)
+    ref = torch.zeros(taps, Kp, N, device="cuda", dtype=dtype)
+    ref[:, :K, :] = wt.permute(2, 1, 0).flip(0).to(dtype)
+    assert torch.equal(ops.pack_conv_weight_dgrad(w, dtype, kpad), ref)
+    if N % 64 == 0 and kpad is None:
+        Ch = N // 4
+        cht = ops.lstm_cht(Ch)
+        b = torch.randn(N, device="cuda", generator=g)
+        got, gb = ops.pack_lstm_weight(w, b, dtype)
+        ref = wt.reshape(4, Ch // cht, cht, K, taps).permute(4, 1, 0, 2, 3).reshape(taps, N, K).to(dtype)
+        assert torch.equal(got, ref)
+        assert torch.equal(gb, b.reshape(4, Ch // cht, cht).permute(1, 0, 2).reshape(N))
+    dw = torch.randn(taps, N, Kp, device="cuda", generator=g)
+    assert torch.equal(ops.unpack_conv_wgrad(dw, K), dw[:, :, :K].permute(1, 2, 0).reshape(N, K, ks, ks))
+
+
+@pytest.mark.parametrize("Cin,Cout", [(128, 64), (40, 24), (1024, 512)])
+def test_convT_weight_pack_exact(Cin, Cout):
+    from unet_convlstm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(Cin)
+    w = torch.randn(Cin, Cout, 2, 2, device="cuda", generator=g)
+    fwd, bwd = ops.pack_convT_weight(w, torch.bfloat16)
+    wt = w.reshape(Cin, Cout, 4)
+    assert torch.equal(fwd, wt.permute(2, 1, 0).reshape(1, 4 * Cout, Cin).bfloat16())
+    assert torch.equal(bwd, wt.permute(0, 2, 1).reshape(1, Cin, 4 * Cout).bfloat16())

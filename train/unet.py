@@ -124,6 +124,7 @@ class DoubleConv(nn.Module):
             # inference (model.eval() under torch.no_grad()): BatchNorm folded into the conv epilogue -- one kernel
             # per conv instead of conv + finalize + normalise/ReLU pass
             K = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
+            self._caches[i].begin_forward(False)
             wp = self._caches[i].get(("fwd", x0.dtype, K), (conv.weight,),
                                      lambda: ops.pack_conv_weight(conv.weight, x0.dtype, K))
             scale, shift = self._caches[i].get(

@@ -12,24 +12,35 @@ from . import ops
 
 
 class WeightCache:
-    """Packed (GEMM-layout, activation-dtype) copies of a module's parameters, rebuilt when the
-    parameter changes (optimizer step / load_state_dict bump the tensor version)."""
+    """Packed (GEMM-layout, activation-dtype) copies of a module's parameters, rebuilt when the parameter changes.
+    Two signals: the tensor version (in-place torch ops, load_state_dict, this package's optimizer), and -- because
+    torch's FUSED optimizers (`torch._fused_adamw_` ...) update parameters WITHOUT touching the version counter -- a
+    completed backward pass: the first differentiated forward after a backward through the module starts from an
+    empty cache (a parameter update can only follow a backward; re-packing is ~1 % of a training step)."""
 
     def __init__(self):
         self._d = {}
         self._open = 0        # forward passes (with a graph) whose backward has not run yet
         self._shared = False  # the parameters were used more than once in the graph(s) still open
+        self._dirty = False   # a backward ran since the cache was filled: an optimizer may have stepped
 
-    def note_forward(self):
-        self._open += 1
-        if self._open > 1:
-            self._shared = True
+    def begin_forward(self, differentiated: bool) -> bool:
+        """Call at the top of every forward pass, BEFORE the first get().  Returns `differentiated`."""
+        if self._dirty:
+            self._d.clear()
+            self._dirty = False
+        if differentiated:
+            self._open += 1
+            if self._open > 1:
+                self._shared = True
+        return differentiated
 
     def note_backward(self) -> bool:
         """True if this backward is the ONLY gradient contribution the parameters receive in this pass (autograd sums
         several contributions on the current stream, which rules out producing one of them on the background
         stream, ops.background)."""
         single = not self._shared
+        self._dirty = True
         self._open = max(0, self._open - 1)
         if self._open == 0:
             self._shared = False
@@ -53,11 +64,9 @@ def _c(t):
 
 
 def _count_use(ctx, cache) -> bool:
-    """Registers a forward pass that will be differentiated (see WeightCache.note_backward)."""
-    if any(ctx.needs_input_grad):
-        cache.note_forward()
-        return True
-    return False
+    """Top of a Function.forward: drops packed weights a finished backward (hence possibly an optimizer step) has
+    outdated, and registers the pass if it will be differentiated (see WeightCache.note_backward)."""
+    return cache.begin_forward(any(ctx.needs_input_grad))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -100,6 +109,7 @@ class ConvBnRelu(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, momentum, cache):
+        ctx.counted = _count_use(ctx, cache)
         x0 = _c(x0)
         x1 = None if x1 is None else _c(x1)
         dt = x0.dtype
@@ -118,7 +128,6 @@ class ConvBnRelu(torch.autograd.Function):
             ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
             ctx.tstride = stats[4]
             ctx.training, ctx.cache, ctx.has_bias, ctx.first = training, cache, bias is not None, True
-            ctx.counted = _count_use(ctx, cache)
             return y
         ctx.first = False
         wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
@@ -133,7 +142,6 @@ class ConvBnRelu(torch.autograd.Function):
         ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
         ctx.tstride = stats[4]
         ctx.training, ctx.cache, ctx.has_bias = training, cache, bias is not None
-        ctx.counted = _count_use(ctx, cache)
         return y
 
     @staticmethod
@@ -187,13 +195,7 @@ class ConvBnRelu(torch.autograd.Function):
 
 def _dgrad_pack_padded(weight, dt, Kp):
     """Data-gradient weights [taps, Kp, N]; rows >= K (zero-padded input channels) stay zero."""
-    N, K = weight.shape[0], weight.shape[1]
-    if Kp == K:
-        return ops.pack_conv_weight_dgrad(weight, dt)
-    full = torch.zeros((weight.shape[2] * weight.shape[3], Kp, N), device=weight.device, dtype=dt)
-    packed = ops.pack_conv_weight_dgrad(weight, dt)
-    ops.copy_(full[:, :K, :], packed)
-    return full
+    return ops.pack_conv_weight_dgrad(weight, dt, Kp)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -248,6 +250,7 @@ class ConvT2x2(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, Hd, Wd, cache):
+        ctx.counted = _count_use(ctx, cache)
         x = _c(x)
         dt = x.dtype
         T, B, H, W, Cin = x.shape
@@ -256,7 +259,6 @@ class ConvT2x2(torch.autograd.Function):
         y = ops.convT2x2_fwd(x, wf, bias.detach() if bias is not None else None, Cout, Hd, Wd)
         ctx.save_for_backward(x, weight)
         ctx.cache, ctx.has_bias, ctx.bias = cache, bias is not None, bias
-        ctx.counted = _count_use(ctx, cache)
         return y
 
     @staticmethod
@@ -318,6 +320,7 @@ class ConvLSTMSeq(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_seq, h0, c0, weight, bias, cache):
+        ctx.counted = _count_use(ctx, cache)
         x_seq = _c(x_seq)
         dt = x_seq.dtype
         T, B, H, W, Cin = x_seq.shape
@@ -357,7 +360,6 @@ class ConvLSTMSeq(torch.autograd.Function):
         ctx.save_for_backward(x_seq, weight)
         ctx.h_all, ctx.c_all, ctx.gates = h_all, c_all, gates
         ctx.have_h0, ctx.cache, ctx.has_bias, ctx.bias = have_h0, cache, bias is not None, bias
-        ctx.counted = _count_use(ctx, cache)
         h_seq = h_all[1:]
         c_T = c_all[T]
         ctx.mark_non_differentiable()

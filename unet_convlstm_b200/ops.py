@@ -43,6 +43,13 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def bump_version(*tensors):
+    """Marks tensors our kernels modified in place through raw pointers (torch cannot see those writes)."""
+    for t in tensors:
+        if t is not None:
+            torch.autograd.graph.increment_version(t)
+
+
 def _st():
     return torch.cuda.current_stream().cuda_stream
 
@@ -109,24 +116,43 @@ def lstm_cht(Ch: int) -> int:
     return 64 if Ch % 64 == 0 else (32 if Ch % 32 == 0 else (16 if Ch % 16 == 0 else 0))
 
 
+def _pack_ok(w: torch.Tensor, taps: int) -> bool:
+    return w.dtype == torch.float32 and taps <= 9 and w.is_cuda
+
+
+def _pack(w, A, B, taps, out, a_contig, flip, tap_pitch, row_pitch, perm_ch=0, perm_cht=0):
+    """b200_pack_weight: tiled layout change [A][B][taps] fp32 -> GEMM operand (see include/b200_convlstm.h)."""
+    src = w.detach()
+    src = src if src.is_contiguous() else src.contiguous()
+    _lib.call("b200_pack_weight", _p(src), A, B, taps, _p(out), _f32(out), int(a_contig), int(flip), tap_pitch,
+              row_pitch, perm_ch, perm_cht, _st())
+    return out
+
+
 def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, kpad: int | None = None) -> torch.Tensor:
     """OIHW fp32 [N, K, k, k] -> [k*k, N, Kp] (K contiguous: the GEMM B operand, K-major)."""
     N, K, kh, kw = w.shape
     taps = kh * kw
     Kp = K if kpad is None else kpad
     out = (torch.zeros if Kp != K else torch.empty)((taps, N, Kp), device=w.device, dtype=dtype)
+    if _pack_ok(w, taps):
+        return _pack(w, N, K, taps, out, False, False, N * Kp, Kp)
     copy_(out[:, :, :K], w.detach().reshape(N, K, taps).permute(2, 0, 1))
     return out
 
 
-def pack_conv_weight_dgrad(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """OIHW [N, K, k, k] -> [k*k (flipped), K, N]: the weights of the data-gradient convolution."""
+def pack_conv_weight_dgrad(w: torch.Tensor, dtype: torch.dtype, kpad: int | None = None) -> torch.Tensor:
+    """OIHW [N, K, k, k] -> [k*k (flipped), Kp, N]: the weights of the data-gradient convolution (rows >= K, the
+    zero-padded input channels, stay zero)."""
     N, K, kh, kw = w.shape
     taps = kh * kw
-    out = torch.empty((taps, K, N), device=w.device, dtype=dtype)
+    Kp = K if kpad is None else kpad
+    out = (torch.zeros if Kp != K else torch.empty)((taps, Kp, N), device=w.device, dtype=dtype)
+    if _pack_ok(w, taps):
+        return _pack(w, N, K, taps, out, True, True, Kp * N, N)
     # out[taps-1-tap][k][n] = w[n][k][tap]: the tap dimension runs backwards in the destination
-    _copy_raw(out, (taps - 1) * K * N, w.detach(), 0,
-              [(taps, 1, -K * N), (K, taps, N), (N, K * taps, 1)])
+    _copy_raw(out, (taps - 1) * Kp * N, w.detach(), 0,
+              [(taps, 1, -Kp * N), (K, taps, N), (N, K * taps, 1)])
     return out
 
 
@@ -138,10 +164,13 @@ def pack_lstm_weight(w: torch.Tensor, b: torch.Tensor | None, dtype: torch.dtype
     cht = lstm_cht(Ch)
     nt = Ch // cht
     out = torch.empty((taps, N, K), device=w.device, dtype=dtype)
-    # views [taps, nt, g, j, K]
-    dst = out.view(taps, nt, 4, cht, K)
-    src = w.detach().reshape(4, nt, cht, K, taps).permute(4, 1, 0, 2, 3)
-    copy_(dst, src)
+    if _pack_ok(w, taps):
+        _pack(w, N, K, taps, out, False, False, N * K, K, Ch, cht)
+    else:
+        # views [taps, nt, g, j, K]
+        dst = out.view(taps, nt, 4, cht, K)
+        src = w.detach().reshape(4, nt, cht, K, taps).permute(4, 1, 0, 2, 3)
+        copy_(dst, src)
     bp = None
     if b is not None:
         bp = torch.empty(N, device=w.device, dtype=torch.float32)
@@ -154,8 +183,12 @@ def pack_convT_weight(w: torch.Tensor, dtype: torch.dtype):
     and data-gradient operand [1, Cin, 4*Cout]."""
     Cin, Cout = w.shape[0], w.shape[1]
     fwd = torch.empty((1, 4 * Cout, Cin), device=w.device, dtype=dtype)
-    copy_(fwd.view(4, Cout, Cin), w.detach().reshape(Cin, Cout, 4).permute(2, 1, 0))
     bwd = torch.empty((1, Cin, 4 * Cout), device=w.device, dtype=dtype)
+    if _pack_ok(w, 4):
+        _pack(w, Cin, Cout, 4, fwd, True, False, Cout * Cin, Cin)      # fwd[(tap, co)][ci] = w[ci][co][tap]
+        _pack(w, Cin, Cout, 4, bwd, False, False, Cout, 4 * Cout)      # bwd[ci][(tap, co)] = w[ci][co][tap]
+        return fwd, bwd
+    copy_(fwd.view(4, Cout, Cin), w.detach().reshape(Cin, Cout, 4).permute(2, 1, 0))
     copy_(bwd.view(Cin, 4, Cout), w.detach().reshape(Cin, Cout, 4).permute(0, 2, 1))
     return fwd, bwd
 
@@ -165,6 +198,9 @@ def unpack_conv_wgrad(dw: torch.Tensor, K: int) -> torch.Tensor:
     taps, N, Kp = dw.shape
     k = int(round(taps ** 0.5))
     g = torch.empty((N, K, k, k), device=dw.device, dtype=torch.float32)
+    if dw.dtype == torch.float32 and dw.is_contiguous() and taps <= 9:
+        _lib.call("b200_unpack_wgrad", _p(dw), N, K, taps, Kp, _p(g), _st())
+        return g
     copy_(g.view(N, K, taps), dw[:, :, :K].permute(1, 2, 0))
     return g
 
@@ -320,6 +356,9 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
                       tag=f"C{C} {H}x{W}", work=(None, z.numel() * z.element_size()))
         _lib.call("b200_bn_finalize", _p(ws[0]), _p(ws[1]), T, P, C, _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), eps, momentum, 1, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
+        # the kernel wrote the running estimates through raw pointers: tell autograd's version counters, which
+        # the folded-BatchNorm cache of the inference path (and anyone else) relies on
+        bump_version(running_mean, running_var)
     else:
         _lib.call("b200_bn_finalize", None, None, 1, P, C, _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), eps, momentum, 0, _p(mean), _p(rstd), _p(scale), _p(shift), _st())

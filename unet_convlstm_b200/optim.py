@@ -16,7 +16,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .ops import _p, _st
+from .ops import _p, _st, bump_version
 
 
 def _ptr_array(tensors):
@@ -70,6 +70,7 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     sq = grad_sqnorm(grads)
     for gs in _chunks(grads):
         _lib.call("b200_grad_clip_multi", len(gs), _ptr_array(gs), _numel_array(gs), _p(sq), float(max_norm), _st())
+    bump_version(*grads)
     return sq.sqrt().float()
 
 
@@ -129,4 +130,5 @@ class AdamW(torch.optim.Optimizer):
                 _lib.call("b200_adamw_multi", len(P), _ptr_array(P), _ptr_array(G), _ptr_array(M), _ptr_array(V),
                           _numel_array(P), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                           float(group["weight_decay"]), t, _p(sq), float(clip_max_norm or 0.0), _st())
+                bump_version(*P, *M, *V)  # written through raw pointers: packed-weight caches key on the version
         return loss
