@@ -234,3 +234,83 @@ def test_metrics_oracle_matches_reference_evaluate(golden_dir):
     tmin, tmax, scale = z["asinh.params"]
     assert MO.epoch_metrics([(p, y, m)], tmin, tmax, scale, "asinh") == (0.0, 0.0, 0.0)
     assert tuple(z["empty.result"][1:]) == (0.0, 0.0, 0.0)
+
+
+def test_optimizer_oracle_matches_torch_clip_and_adamw():
+    """oracle/optim_oracle.py against the calls the reference makes (main.py:106, :275), run on the CPU in fp64."""
+    import torch
+    from oracle import optim_oracle as OO
+    rng = np.random.default_rng(9)
+    shapes = [(5, 3), (17,), (2, 3, 3, 3)]
+    ps = [rng.standard_normal(s) for s in shapes]
+    tp = [torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in ps]
+    kw = dict(lr=2e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.03)
+    opt = torch.optim.AdamW(tp, **kw)
+    m = [np.zeros(s) for s in shapes]
+    v = [np.zeros(s) for s in shapes]
+    for step in range(1, 5):
+        gs = [rng.standard_normal(s) * (5.0 if step == 1 else 0.05) for s in shapes]   # a clipping and non-clipping steps
+        for t, g in zip(tp, gs):
+            t.grad = torch.tensor(g, dtype=torch.float64)
+        total_ref = float(torch.nn.utils.clip_grad_norm_(tp, 1.0))
+        total, gc = OO.clip_grad_norm(gs, 1.0)
+        assert abs(total - total_ref) <= 1e-12 * total_ref
+        for t, g in zip(tp, gc):
+            np.testing.assert_allclose(t.grad.numpy(), g, rtol=1e-12, atol=0)
+        opt.step()
+        ps, m, v = OO.adamw_step(ps, gc, m, v, step, **kw)
+        for t, p in zip(tp, ps):
+            np.testing.assert_allclose(t.detach().numpy(), p, rtol=1e-11, atol=1e-14)
+
+
+def test_weight_cache_invalidation_rules():
+    """functional.WeightCache on CPU tensors (pure host logic): version bumps, the emptied cache at the first forward
+    after a backward (torch's fused optimizers do not bump versions), and the single-use bookkeeping that gates the
+    background weight-gradient stream."""
+    import torch
+    from unet_convlstm_b200.functional import WeightCache
+    w = torch.nn.Parameter(torch.zeros(4))
+    c, built = WeightCache(), []
+
+    def get():
+        return c.get("k", (w,), lambda: built.append(1) or len(built))
+
+    c.begin_forward(True)
+    assert get() == 1 and get() == 1                      # cached within a step
+    assert c.note_backward() is True                      # one use of the weights in this graph
+    c.begin_forward(True)                                 # the next step starts from an empty cache
+    assert get() == 2
+    assert c.note_backward() is True
+    c.begin_forward(False)                                # ... and so does an evaluation pass after training
+    assert get() == 3
+    c.begin_forward(False)
+    assert get() == 3                                     # inference keeps its packed weights
+    with torch.no_grad():
+        w.add_(1.0)                                       # an in-place torch op bumps the version
+    assert get() == 4
+    c.begin_forward(True), c.begin_forward(True)          # the module called twice in one graph
+    assert c.note_backward() is False and c.note_backward() is False
+    c.begin_forward(True)
+    assert c.note_backward() is True                      # and alone again
+
+
+def test_background_stream_guards_on_leaf_state():
+    """ops._leaf_takes_gradient_as_is: the background path is only safe when autograd merely stores the gradient."""
+    import torch
+    from unet_convlstm_b200 import ops
+    p = torch.nn.Parameter(torch.zeros(3))
+    assert ops._leaf_takes_gradient_as_is(p)
+    p.grad = torch.zeros(3)
+    assert not ops._leaf_takes_gradient_as_is(p)          # accumulation into an existing .grad
+    p.grad = None
+    h = p.register_hook(lambda g: g)
+    assert not ops._leaf_takes_gradient_as_is(p)          # a tensor hook reads the gradient during backward
+    h.remove()
+    assert ops._leaf_takes_gradient_as_is(p)
+    h = p.register_post_accumulate_grad_hook(lambda q: None)
+    assert not ops._leaf_takes_gradient_as_is(p)
+    p._b200_bg_aware = True                               # dist.GradReducer orders itself behind the stream
+    assert ops._leaf_takes_gradient_as_is(p)
+    h.remove()
+    assert not ops._leaf_takes_gradient_as_is((p * 2))    # not a leaf
+    assert not ops.background(p).active                   # outside a backward pass

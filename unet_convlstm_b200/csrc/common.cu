@@ -4,7 +4,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace b200 {
 
@@ -48,19 +50,21 @@ int* device_error_flag() {
     return flags[dev];
 }
 
-unsigned* device_sync_counter() {
-    static unsigned* ctrs[64] = {nullptr};
+unsigned* device_sync_counter(cudaStream_t stream) {
+    // one counter per (device, stream): two timestep-persistent kernels on different streams may run side by side
+    static std::map<std::pair<int, cudaStream_t>, unsigned*> ctrs;
     static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    if (!ctrs[dev]) {
+    unsigned*& slot = ctrs[std::make_pair(dev, stream)];
+    if (!slot) {
         unsigned* p = nullptr;
         if (cudaMalloc(&p, sizeof(unsigned)) != cudaSuccess) return nullptr;
         cudaMemset(p, 0, sizeof(unsigned));
-        ctrs[dev] = p;
+        slot = p;
     }
-    return ctrs[dev];
+    return slot;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -29,8 +29,21 @@ void set_last_error(const char* fmt, ...);
     } while (0)
 
 int num_sms();
+
+// first() is true once per device (and call site): cudaFuncSetAttribute settings belong to the device that was
+// current when they were made, so a process driving several GPUs has to repeat them on each.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
 int* device_error_flag();  // one int in device memory, zero unless a watchdog fired
-unsigned* device_sync_counter();  // one step counter per device for the timestep-persistent kernels
+unsigned* device_sync_counter(cudaStream_t stream);  // step counter of the timestep-persistent kernels, per (device, stream)
 
 // ---- TMA tensor-map construction (driver entry point resolved at run time, no libcuda link) ----
 // Activation map over a bf16 NHWC tensor viewed as {C, W, H, B, T}; box = {box_c, Wt, Ht, Bt, 1}.

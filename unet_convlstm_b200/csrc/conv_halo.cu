@@ -480,10 +480,9 @@ template <int BLOCK_N>
 static int launch_halo_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb,
                             const ConvHaloParams& p, int smem_bytes, cudaStream_t stream) {
     auto kern = conv_halo_kernel<BLOCK_N>;
-    static int attr_smem = 0;
-    if (smem_bytes > attr_smem) {
+    static PerDeviceOnce attr_once;  // kernel attributes are per device
+    if (attr_once.first()) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_LIMIT));
-        attr_smem = H_SMEM_LIMIT;
     }
     const int total = p.num_m_tiles * p.num_n_tiles;
     const int grid = total < num_sms() ? total : num_sms();

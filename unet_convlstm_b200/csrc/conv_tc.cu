@@ -698,11 +698,10 @@ static int launch_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
                        const ConvTcParams& p, cudaStream_t stream) {
     using Cfg = TcCfg<BLOCK_N>;
     auto kern = conv_tc_kernel<BLOCK_N, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;  // kernel attributes are per device
+    if (attr_once.first()) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     int total = p.num_m_tiles * p.num_n_tiles;
     int grid = total < num_sms() ? total : num_sms();
@@ -722,7 +721,7 @@ static int launch_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
 
 int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpacked, ConvTcParams p,
                            cudaStream_t stream) {
-    p.sync_ctr = device_sync_counter();
+    p.sync_ctr = device_sync_counter(stream);
     if (!p.sync_ctr || p.seq_T <= 0) {
         set_last_error("convlstm_seq_tc: no step counter / bad sequence length");
         return B200_ERR_ARG;
@@ -731,7 +730,7 @@ int launch_convlstm_seq_tc(const void* x_seq, const void* h_all, const void* wpa
 }
 
 int launch_convlstm_seq_bwd_tc(const void* wd_packed, ConvTcParams p, cudaStream_t stream) {
-    p.sync_ctr = device_sync_counter();
+    p.sync_ctr = device_sync_counter(stream);
     if (!p.sync_ctr || p.seq_T <= 0 || !p.bwd_dz_all || !p.bwd_gates || !p.bwd_c_all || !p.bwd_dc) {
         set_last_error("convlstm_seq_bwd_tc: missing buffers / bad sequence length");
         return B200_ERR_ARG;

@@ -442,10 +442,9 @@ static int launch_pair_impl(const CUtensorMap& ta0, const CUtensorMap& ta1, cons
                             cudaStream_t stream) {
     using Cfg = Tc2Cfg<BLOCK_N>;
     auto kern = conv_tc2_kernel<BLOCK_N, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;  // kernel attributes are per device
+    if (attr_once.first()) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int max_clusters = num_sms() / 2;
@@ -485,7 +484,7 @@ int launch_conv_tc2(const void* src0, const void* src1, const void* wpacked, Con
         return B200_ERR_ARG;
     }
     if (p.seq_T > 0) {
-        p.sync_ctr = device_sync_counter();
+        p.sync_ctr = device_sync_counter(stream);
         if (!p.sync_ctr) {
             set_last_error("conv_tc2: no step counter");
             return B200_ERR_CUDA;

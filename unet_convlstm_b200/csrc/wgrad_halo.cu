@@ -302,15 +302,14 @@ int launch_wgrad_halo(const void* dz, int Nz, const void* src, int Csrc, int T, 
         return B200_ERR_SHAPE;
     }
     const int smem = p.stages * stage_bytes + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;  // kernel attributes are per device
+    if (attr_once.first()) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // the whole unified L1/shared array as shared memory: the kernel itself only needs its ring, but the
         // remainder lets HBM-bound blocks of another stream (BatchNorm sums: 9 KB static) share the SM when the
         // weight gradient runs on the background stream (with the default carve-out the next step is 196 KB)
         B200_CUDA_CHECK(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     const int total = p.s_tiles * p.splits;
     const int grid = total < nsm ? total : nsm;

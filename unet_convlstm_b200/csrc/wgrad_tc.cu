@@ -416,8 +416,8 @@ static int launch_wgrad_impl(const CUtensorMap& tz, const CUtensorMap& ts, const
                              cudaStream_t stream) {
     using Cfg = WgCfg<BLOCK_N, STACKED>;
     auto kern = wgrad_tc_kernel<BLOCK_N, STACKED>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;  // kernel attributes are per device
+    if (attr_once.first()) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES));
         // the whole unified L1/shared array as shared memory: the kernel itself only needs its ring, but the
@@ -425,7 +425,6 @@ static int launch_wgrad_impl(const CUtensorMap& tz, const CUtensorMap& ts, const
         // weight gradient runs on the background stream (with the default carve-out the next step is 196 KB)
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     int total = p.out_tiles * p.splits;
     int grid = total < num_sms() ? total : num_sms();

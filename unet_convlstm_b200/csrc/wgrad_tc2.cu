@@ -388,15 +388,14 @@ template <int BLOCK_N, bool STACKED>
 static int launch_wgrad2_impl(const CUtensorMap& tz, const CUtensorMap& ts, const Wgrad2Params& p, cudaStream_t stream) {
     using Cfg = Wg2Cfg<BLOCK_N, STACKED>;
     auto kern = wgrad_tc2_kernel<BLOCK_N, STACKED>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;  // kernel attributes are per device
+    if (attr_once.first()) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         // the whole unified L1/shared array as shared memory: the kernel itself only needs its ring, but the
         // remainder lets HBM-bound blocks of another stream (BatchNorm sums: 9 KB static) share the SM when the
         // weight gradient runs on the background stream (with the default carve-out the next step is 196 KB)
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     const int total = p.out_tiles * p.splits;
     const int max_clusters = num_sms() / 2;

@@ -542,7 +542,7 @@ def _leaf_takes_gradient_as_is(p) -> bool:
     """True if autograd will only STORE the new gradient of leaf `p` (no kernel on the current stream reads it during
     backward): .grad is still empty and nobody hooked the tensor -- except hooks that declare themselves aware of the
     background stream (dist.GradReducer sets `_b200_bg_aware`)."""
-    if p.grad is not None or not p.is_leaf:
+    if not p.is_leaf or p.grad is not None:
         return False
     if getattr(p, "_backward_hooks", None):
         return False
