@@ -21,6 +21,8 @@
 // both CTAs by the leader's multicast tcgen05.commit; tempty collects the epilogue warps of the pair.  Work units,
 // reduction splits, the five producer warps and the transposed fp32 red.add epilogue are those of wgrad_tc.cu.
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "ptx.cuh"
 
 namespace b200 {
@@ -40,6 +42,7 @@ struct Wgrad2Params {
     int num_rblocks, rb_per_split, splits;
     int G;                      // taps per CTA and group (128 / Csrc); a pair group has 2G taps
     int ngroups, GU, ngsets;
+    int gset_inner;             // unit order: tap sets fastest (1) or slowest (0)
     int s_tiles, v_tiles, out_tiles;
     float* dw;
     long long ldk;
@@ -75,10 +78,21 @@ __device__ __forceinline__ Wg2Unit wg2_decode(const Wgrad2Params& p, int unit) {
     Wg2Unit u;
     u.split = unit / p.out_tiles;
     int ot = unit - u.split * p.out_tiles;
-    const int vt = ot % p.v_tiles;
-    ot /= p.v_tiles;
-    const int st = ot % p.s_tiles;
-    u.gset = ot / p.s_tiles;
+    int vt, st;
+    if (p.gset_inner) {
+        // tap sets fastest: the pairs resident at the same time then cover ALL taps of a few (dz tile, source tile)
+        // pairs -- the taps read the same source bytes (shifted windows) and the same dz tile -- instead of one tap
+        // set of every tile, which re-reads the whole dz range once per tap set (5 x at the temporal cell's shape)
+        u.gset = ot % p.ngsets;
+        ot /= p.ngsets;
+        vt = ot % p.v_tiles;
+        st = ot / p.v_tiles;
+    } else {
+        vt = ot % p.v_tiles;
+        ot /= p.v_tiles;
+        st = ot % p.s_tiles;
+        u.gset = ot / p.s_tiles;
+    }
     u.s0 = st * (STACKED ? BLOCK_N : 2 * W2_BLOCK_M);  // stacked: dz channels are N; normal: 256 dz rows per pair
     u.v0 = vt * BLOCK_N;
     u.ngr = min(p.GU, p.ngroups - u.gset * p.GU);
@@ -456,6 +470,10 @@ int launch_wgrad_tc2(const void* dz, int Nz, const void* src, int Csrc, int T, i
     p.ngsets = (p.ngroups + p.GU - 1) / p.GU;
     p.GU = (p.ngroups + p.ngsets - 1) / p.ngsets;
     p.out_tiles = p.ngsets * p.s_tiles * p.v_tiles;
+    {
+        static const int order = [] { const char* e = getenv("B200_WGRAD_TAPS_INNER"); return e ? atoi(e) : 1; }();
+        p.gset_inner = order;
+    }
     // reduction split over the clusters (see wgrad_tc.cu): fewest waves per split, at least 4 blocks per unit
     const int ncl = num_sms() / 2;
     int max_splits = (p.num_rblocks + 3) / 4;
