@@ -102,7 +102,9 @@ class ConvLSTM(nn.Module):
         out_nchw = Fn.permute_cast(out, (0, 1, 4, 2, 3), torch.float32)
         new_states = [(Fn.permute_cast(h, (0, 3, 1, 2), torch.float32), Fn.permute_cast(c, (0, 3, 1, 2), torch.float32))
                       for h, c in finals]
-        return [out_nchw[t] for t in range(T)], new_states
+        # unbind, not T x select: the backward of unbind stacks the T frame gradients in one pass, T selects would
+        # each materialise a full-size zero tensor and autograd would add the T of them
+        return list(out_nchw.unbind(0)), new_states
 
 
 # -----------------------------------------------------------------------------------------------
@@ -278,11 +280,13 @@ class TemporalUNetDualView(nn.Module):
         d0 = self.up0._seq(d1, x0)
         y = self.outc._seq(d0)  # fp32 [T,B,H,W,out]
 
+        # list of T frames as views of one buffer.  unbind, not T x select: the backward of unbind stacks the T frame
+        # gradients in one pass; T selects each materialise a full-size zero tensor that autograd then adds up
+        # (59 element-wise launches over the whole output map per step at T = 20)
         if y.shape[-1] == 1:
-            out_seq = [y[t].view(B, 1, H, W) for t in range(T)]  # C == 1: NHWC and NCHW coincide
+            out_seq = list(y.view(T, B, 1, H, W).unbind(0))  # C == 1: NHWC and NCHW coincide
         else:
-            yn = Fn.permute_cast(y, (0, 1, 4, 2, 3), torch.float32)
-            out_seq = [yn[t] for t in range(T)]
+            out_seq = list(Fn.permute_cast(y, (0, 1, 4, 2, 3), torch.float32).unbind(0))
         new_state = [(Fn.permute_cast(h, (0, 3, 1, 2), torch.float32), Fn.permute_cast(c, (0, 3, 1, 2), torch.float32))
                      for h, c in finals]
         return out_seq, new_state
