@@ -6,6 +6,11 @@
     ops.py         tensor-level wrappers (allocation, dispatch tensor-core vs CUDA-core)
     functional.py  autograd Functions (hand-derived backward of the reference modules)
     dist.py        data-parallel gradient all-reduce (NCCL, bucketed, overlapped with backward)
+    loss.py        the reference's compute_loss as two fused kernels
+    optim.py       clip_grad_norm_ + AdamW as multi-tensor kernels
+    loop.py        train_one_epoch / evaluate with on-device metric accumulators
+    data.py        pinned, double-buffered host->device prefetch
+    graph.py       optional CUDA-graph replay of the training step
 
 The reference-facing module surface is train/unet.py at the repository root.
 """
