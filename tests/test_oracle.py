@@ -314,3 +314,47 @@ def test_background_stream_guards_on_leaf_state():
     h.remove()
     assert not ops._leaf_takes_gradient_as_is((p * 2))    # not a leaf
     assert not ops.background(p).active                   # outside a backward pass
+
+
+def test_epoch_loop_batch_staging_order(monkeypatch):
+    """loop._device_batches (host logic only): every batch is yielded exactly once and in order, the copy of
+    batch i+1 is started BEFORE batch i is handed to the step, device batches pass through untouched, an empty
+    loader yields nothing."""
+    from unet_convlstm_b200 import loop
+
+    class FakeTensor:
+        def __init__(self, tag, cuda=False):
+            self.tag, self.is_cuda = tag, cuda
+
+        def is_pinned(self):
+            return True
+
+    events = []
+
+    class FakePrefetcher:
+        def __init__(self, device):
+            self.pending = None
+
+        def start(self, *ts):
+            events.append(("start", ts[0].tag))
+            self.pending = ts
+
+        def get(self):
+            ts, self.pending = self.pending, None
+            events.append(("get", ts[0].tag))
+            return [FakeTensor(t.tag, cuda=True) for t in ts]
+
+    monkeypatch.setattr(loop, "DevicePrefetcher", FakePrefetcher)
+    host = [(FakeTensor(i), FakeTensor(i), FakeTensor(i)) for i in range(4)]
+    seen = []
+    for x, y, m in loop._device_batches(host, "cuda"):
+        events.append(("step", x.tag))
+        seen.append(x.tag)
+        assert x.is_cuda
+    assert seen == [0, 1, 2, 3]
+    assert events == [("start", 0), ("get", 0), ("start", 1), ("step", 0), ("get", 1), ("start", 2), ("step", 1),
+                      ("get", 2), ("start", 3), ("step", 2), ("get", 3), ("step", 3)]
+    events.clear()
+    dev = [(FakeTensor(i, True), FakeTensor(i, True), FakeTensor(i, True)) for i in range(2)]
+    assert [b[0].tag for b in loop._device_batches(dev, "cuda")] == [0, 1] and events == []
+    assert list(loop._device_batches([], "cuda")) == []
