@@ -3,8 +3,10 @@
  * The reference (dordanino12/unet-convlstm) has no native interface: its hot path is the Python
  * nn.Module code in train/unet.py, which lowers to ATen library kernels.  Each entry point below
  * names the reference lines whose arithmetic it replaces.  Conventions:
- *   - every pointer is a device pointer owned by the caller; nothing is allocated or freed here
- *     except one 4-byte per-device watchdog flag;
+ *   - every pointer is a device pointer owned by the caller (the multi-tensor entry points take HOST arrays of
+ *     device pointers and say so); nothing is allocated or freed here except one 4-byte watchdog flag per device
+ *     and one 4-byte step counter per (device, stream) that runs a timestep-persistent kernel;
+ *   - calls on distinct streams may be made concurrently from different threads;
  *   - activations are NHWC ("channels last"), bf16 on the tensor-core path (*_tc), fp32 or bf16 on
  *     the generic SIMT path; a sequence tensor is [T][B][H][W][C];
  *   - `stream` is a cudaStream_t passed as void*; kernels are launched on it, no hidden sync;
