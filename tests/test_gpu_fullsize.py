@@ -187,14 +187,16 @@ def test_model_large_images_vs_oracle(size, base_ch, B, T):
 @pytest.mark.parametrize("H,W,B,T", [(40, 28, 2, 2),    # 40 -> 20 -> 10 -> 5 -> 2: floor pooling at 5x3, F.pad in up3
                                      (50, 34, 1, 3),    # odd at every level below the first: 25x17, 12x8, 6x4, 3x2
                                      (36, 52, 2, 1)])   # 9x13 -> 4x6 -> 2x3, T = 1
-def test_model_ragged_image_sizes_vs_oracle(H, W, B, T):
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_model_ragged_image_sizes_vs_oracle(H, W, B, T, mode):
     """Image sizes that are NOT multiples of 16 through the whole model: MaxPool2d floors (unet.py:81), every Up pads
     its transposed convolution to the skip size (unet.py:95-97), the pooled-gradient accumulation into the skip
     gradient meets rows / columns no pooling window covers, and none of these widths can use the tensor-core tiling
     everywhere.  fp32 check mode against the fp64 CPU oracle: output 1e-5, gradients 2e-4 (or 4x the reference's own
-    fp32 floor: train-mode BatchNorm at 2x1 .. 3x2 spatial is ill-conditioned)."""
+    fp32 floor: train-mode BatchNorm at 2x1 .. 3x2 spatial is ill-conditioned).  bf16 mode (tensor-core
+    kernels where the level's shape tiles, CUDA-core kernels elsewhere): the criterion of test_model_tc_vs_oracle."""
     import unet_convlstm_b200 as pkg
-    from test_gpu_parity import _port_run, rel2 as rel2n
+    from test_gpu_parity import _port_run, close, rel, rel2 as rel2n
     from train.unet import TemporalUNetDualView
     torch.manual_seed(H)
     m = TemporalUNetDualView(base_ch=4, use_skip_lstm=True)
@@ -204,7 +206,7 @@ def test_model_ragged_image_sizes_vs_oracle(H, W, B, T):
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     ref = _port_run(sd, x, dy, torch.float64, False, True)
     r32 = _port_run(sd, x, dy, torch.float32, False, True)
-    pkg.set_precision("fp32")
+    pkg.set_precision(mode)
     m = m.cuda().train()
     xg = torch.from_numpy(x).cuda().requires_grad_(True)
     out, _ = m(xg)
@@ -213,11 +215,19 @@ def test_model_ragged_image_sizes_vs_oracle(H, W, B, T):
     got = {"y": _np(y), "dx": _np(xg.grad)}
     got.update({"g." + k: _np(p.grad) for k, p in m.named_parameters()})
     bad = []
-    for k, v in ref.items():
-        if np.abs(v).max() < 1e-9:
-            continue
-        e = rel2n(got[k], v)
-        tol = max(1e-5 if k == "y" else 2e-4, 4 * rel2n(r32[k], v))
-        if not e < tol:
-            bad.append((k, e, tol))
-    assert not bad, bad
+    keys = [k for k, v in ref.items() if np.abs(v).max() >= 1e-9]
+    if mode == "fp32":
+        for k in keys:
+            e = rel2n(got[k], ref[k])
+            tol = max(1e-5 if k == "y" else 2e-4, 4 * rel2n(r32[k], ref[k]))
+            if not e < tol:
+                bad.append((k, e, tol))
+    else:
+        r16 = _port_run(sd, x, dy, torch.float32, True, True)
+        floors = {k: np.array([rel(r16[k], ref[k]), rel2n(r16[k], ref[k])]) for k in keys}
+        problem = np.max(np.stack(list(floors.values())), axis=0)
+        for k in keys:
+            ok, err = close(got[k], ref[k], "bf16", floors[k], problem)
+            if not ok:
+                bad.append((k, err))
+    assert not bad, (mode, bad)
