@@ -184,11 +184,13 @@ def test_model_large_images_vs_oracle(size, base_ch, B, T):
         assert not bad, (mode, bad)
 
 
-@pytest.mark.parametrize("H,W,B,T", [(40, 28, 2, 2),    # 40 -> 20 -> 10 -> 5 -> 2: floor pooling at 5x3, F.pad in up3
-                                     (50, 34, 1, 3),    # odd at every level below the first: 25x17, 12x8, 6x4, 3x2
-                                     (36, 52, 2, 1)])   # 9x13 -> 4x6 -> 2x3, T = 1
+@pytest.mark.parametrize("H,W,B,T,base_ch", [
+    (40, 28, 2, 2, 4),     # 40 -> 20 -> 10 -> 5 -> 2: floor pooling at 5x3, F.pad in up3
+    (50, 34, 1, 3, 4),     # odd at every level below the first: 25x17, 12x8, 6x4, 3x2
+    (36, 52, 2, 1, 4),     # 9x13 -> 4x6 -> 2x3, T = 1
+    (40, 32, 2, 2, 16)])   # tensor-core channel counts: 40x32 and 10x8 tile (tcgen05), 20x16 and 5x4 do not (CUDA cores)
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_model_ragged_image_sizes_vs_oracle(H, W, B, T, mode):
+def test_model_ragged_image_sizes_vs_oracle(H, W, B, T, base_ch, mode):
     """Image sizes that are NOT multiples of 16 through the whole model: MaxPool2d floors (unet.py:81), every Up pads
     its transposed convolution to the skip size (unet.py:95-97), the pooled-gradient accumulation into the skip
     gradient meets rows / columns no pooling window covers, and none of these widths can use the tensor-core tiling
@@ -199,7 +201,7 @@ def test_model_ragged_image_sizes_vs_oracle(H, W, B, T, mode):
     from test_gpu_parity import _port_run, close, rel, rel2 as rel2n
     from train.unet import TemporalUNetDualView
     torch.manual_seed(H)
-    m = TemporalUNetDualView(base_ch=4, use_skip_lstm=True)
+    m = TemporalUNetDualView(base_ch=base_ch, use_skip_lstm=True)
     rng = np.random.default_rng(H * W)
     x = (rng.random((B, T, 2, H, W)) * 2).astype(np.float32)
     dy = rng.standard_normal((B, T, 1, H, W)).astype(np.float32)
