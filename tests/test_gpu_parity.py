@@ -1042,3 +1042,53 @@ def test_convT_weight_pack_exact(Cin, Cout):
     wt = w.reshape(Cin, Cout, 4)
     assert torch.equal(fwd, wt.permute(2, 1, 0).reshape(1, 4 * Cout, Cin).bfloat16())
     assert torch.equal(bwd, wt.permute(0, 2, 1).reshape(1, Cin, 4 * Cout).bfloat16())
+
+
+def _torch_convlstm(w, b, xs, ks):
+    """Plain PyTorch fp64 reference of ConvLSTM (one layer, zero initial state): unet.py:21-36 over the t loop."""
+    Ch = w.shape[0] // 4
+    B, _, H, W = xs[0].shape
+    h = torch.zeros(B, Ch, H, W, dtype=torch.float64)
+    c = torch.zeros_like(h)
+    outs = []
+    for x in xs:
+        gates = torch.nn.functional.conv2d(torch.cat([x, h], dim=1), w, b, padding=ks // 2)
+        i, f, g, o = torch.chunk(gates, 4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    return outs, (h, c)
+
+
+@pytest.mark.parametrize("ks,cin,ch", [(5, 6, 8), (1, 16, 16), (5, 16, 32)])
+def test_convlstm_other_kernel_sizes(ks, cin, ch):
+    """kernel_size 5 (25 taps: beyond the tiled weight-pack kernel, generic strided pack) and 1, fp32 check mode
+    and bf16 mode, against a plain PyTorch fp64 ConvLSTM: outputs, final state, input and parameter gradients."""
+    import unet_convlstm_b200 as pkg
+    from train.unet import ConvLSTM
+    torch.manual_seed(ks + ch)
+    m = ConvLSTM(cin, ch, num_layers=1, kernel_size=ks)
+    w = m.layers[0].conv.weight.detach().double().requires_grad_(True)
+    b = m.layers[0].conv.bias.detach().double().requires_grad_(True)
+    B, T, H, W = 2, 3, 16, 16
+    g = torch.Generator().manual_seed(ks)
+    xs = [torch.randn(B, cin, H, W, generator=g) for _ in range(T)]
+    dout = [torch.randn(B, ch, H, W, generator=g) for _ in range(T)]
+    xr = [x.double().requires_grad_(True) for x in xs]
+    outs, (hT, cT) = _torch_convlstm(w, b, xr, ks)
+    (sum((o * d.double()).sum() for o, d in zip(outs, dout)) + cT.sum()).backward()
+    m = m.cuda()
+    try:
+        for mode, tol_y, tol_g in (("fp32", 1e-5, 1e-4), ("bf16", 2e-2, 3e-2)):
+            pkg.set_precision(mode)
+            m.zero_grad(set_to_none=True)
+            xg = [x.cuda().requires_grad_(True) for x in xs]
+            out, st = m(xg)
+            (sum((o * d.cuda()).sum() for o, d in zip(out, dout)) + st[0][1].sum()).backward()
+            assert rel2(_np(torch.stack(out)), torch.stack(outs).detach().numpy()) < tol_y, mode
+            assert rel2(_np(st[0][0]), hT.detach().numpy()) < tol_y and rel2(_np(st[0][1]), cT.detach().numpy()) < tol_y
+            assert rel2(np.stack([_np(x.grad) for x in xg]), np.stack([x.grad.numpy() for x in xr])) < tol_g, mode
+            assert rel2(_np(m.layers[0].conv.weight.grad), w.grad.numpy()) < tol_g, mode
+            assert rel2(_np(m.layers[0].conv.bias.grad), b.grad.numpy()) < tol_g, mode
+    finally:
+        pkg.set_precision("bf16")
