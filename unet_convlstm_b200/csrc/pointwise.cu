@@ -217,8 +217,10 @@ static int launch_colreduce(const Op& op, int T_, long long P, int C, int V, dou
     g.cvb = CV < 256 ? CV : 256;
     g.rows_per_iter = 256 / g.cvb;
     const unsigned gy = (CV + g.cvb - 1) / g.cvb;
-    // aim for ~8 blocks per SM in total, at least 4 iterations per thread
-    long long want_x = (8LL * num_sms() + (long long)gy * T_ - 1) / ((long long)gy * T_);
+    // at most 8 blocks per SM in total (= two full waves at 4 resident blocks per SM; rounding UP here gave 1200 blocks
+    // on 1184 slots at T = 20, i.e. a third, almost empty wave: ncu showed the SMs idle for 21 % of the kernel), at
+    // least 4 iterations per thread
+    long long want_x = (8LL * num_sms()) / ((long long)gy * T_);
     long long max_x = (P + 4LL * g.rows_per_iter - 1) / (4LL * g.rows_per_iter);
     if (want_x > max_x) want_x = max_x;
     if (want_x < 1) want_x = 1;
