@@ -12,8 +12,9 @@ are all-reduced over NCCL, overlapped with backward.
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step through the public
 nn.Module API with the batch in pinned host memory (H2D inside the timed region, loss read back).
 `roofline`: the fused ConvLSTM gate-conv kernel, timed per launch with CUDA events inside the timed
-region.  `cpu_baseline`: the reference's CPU path (oracle/torch_port.py: the reference's own ATen
-operators, functional restatement) on this box's host cores, on a bounded sample.
+region.  `cpu_baseline` / `--impl reference`: the UNMODIFIED reference (its train/unet.py model and main.py
+compute_loss, from /root/reference or the git-ignored copy baseline/_ref that travels to the GPU box; kind
+"reference") on this box's host cores, on a bounded sample; oracle/torch_port.py (kind "port") only if no copy exists.
 """
 from __future__ import annotations
 
@@ -139,22 +140,69 @@ def host_info():
 # ------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle/torch_port.py) -- cpu_baseline leg and --impl reference
 # ------------------------------------------------------------------------------------------------
+def load_reference():
+    """The UNMODIFIED reference (train/unet.py's TemporalUNetDualView, main.py's compute_loss) from /root/reference or
+    its git-ignored copy baseline/_ref (made by __graft_entry__.build(); it travels to the GPU box).  Loaded by file
+    path under private module names, so this repository's own `train.unet` stays what `import train.unet` means.
+    Returns (model class, compute_loss, source dir) or None when neither directory exists."""
+    import importlib.util
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import run_reference as RR
+        ref = RR.reference_root()
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        sys.path.pop(0)
+    RR.install_stubs()  # train/resnet18.py (imported by main.py) needs segmentation_models_pytorch
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    ref_unet = load("b200_reference_unet", "train/unet.py")
+    if ref not in sys.path:
+        sys.path.append(ref)  # main.py: `from train.resnet18 import ...` (namespace package `train`)
+    ref_main = load("b200_reference_main", "main.py")
+    return ref_unet.TemporalUNetDualView, ref_main.compute_loss, ref
+
+
 def cpu_reference_run(args, steps, warmup, batch):
-    from oracle import torch_port as TP
-    from train.unet import TemporalUNetDualView
+    """The reference's training step (main.py:94-108) on the host cores.  kind "reference": the reference's own
+    modules (load_reference); kind "port": oracle/torch_port.py, only when no copy of the reference is available."""
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    sd = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).state_dict()
-    p = TP.params_from_state_dict(sd, torch.float32)
-    opt = torch.optim.AdamW([v for v in p.values() if v.requires_grad], lr=1e-3, weight_decay=1e-4)
     x, y, mask = make_batch(batch, args.seq_len, args.size, 1234)
-    params = [v for v in p.values() if v.requires_grad]
+    loaded = load_reference()
+    if loaded is not None:
+        Model, ref_loss, src = loaded
+        model = Model(base_ch=args.base_ch, use_skip_lstm=True).train()
+        params = list(model.parameters())
+        kind = "reference"
+
+        def fwd_loss():
+            out, _ = model(x)
+            return ref_loss(torch.stack(out, dim=1), y, mask)
+    else:
+        from oracle import torch_port as TP
+        from train.unet import TemporalUNetDualView
+        sd = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).state_dict()
+        p = TP.params_from_state_dict(sd, torch.float32)
+        params = [v for v in p.values() if v.requires_grad]
+        kind, src = "port", "oracle/torch_port.py"
+
+        def fwd_loss():
+            out, _ = TP.temporal_unet(p, x, None, training=True)
+            return loss_torch(torch.stack(out, dim=1), y, mask)
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        out, _ = TP.temporal_unet(p, x, None, training=True)
-        loss = loss_torch(torch.stack(out, dim=1), y, mask)
+        loss = fwd_loss()
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
@@ -166,7 +214,7 @@ def cpu_reference_run(args, steps, warmup, batch):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return batch / dt, dt, cores
+    return batch / dt, dt, cores, kind, src
 
 
 def run_reference_arm(args, out):
@@ -175,14 +223,14 @@ def run_reference_arm(args, out):
         return
     # bounded sample: 4 sequences per step (2 when many steps are asked for) so the run ends in minutes
     batch = 4 if args.steps + args.warmup <= 10 else 2
-    value, dt, cores = cpu_reference_run(args, args.steps, args.warmup, batch)
+    value, dt, cores, kind, src = cpu_reference_run(args, args.steps, args.warmup, batch)
     cpu_model, _ = host_info()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, batch_per_step=batch),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu_model, "source": src,
                          "sample": f"{batch} sequence(s) per step (T={args.seq_len}, {args.size}x{args.size}, base_ch "
                                    f"{args.base_ch} + skip LSTMs), fwd + compute_loss + bwd + clip + AdamW, fp32, torch {torch.__version__} CPU "
                                    f"(oneDNN), {args.steps} timed steps"},
@@ -223,19 +271,19 @@ def run_b200_arm(args, out):
     dev = torch.device("cuda", local)
     pkg.set_precision(args.precision)
     _lib.lib()  # fail loudly if the CUDA library is missing
+    ops.enable_background_wgrad()  # this step reads gradients after backward() (own optimizer / GradReducer)
 
     torch.manual_seed(0)  # identical replicas
     model = TemporalUNetDualView(base_ch=args.base_ch, use_skip_lstm=True).to(dev)
     model.train()
-    use_graph = bool(args.graph) and world == 1
     # B200_OPTIM=torch: torch's foreach clip_grad_norm_ + fused AdamW instead of the multi-tensor kernels of
-    # unet_convlstm_b200/optim.py (A/B switch; a CUDA graph needs torch's capturable step counter)
-    own_optim = os.environ.get("B200_OPTIM", "b200") != "torch" and not use_graph
+    # unet_convlstm_b200/optim.py (A/B switch)
+    own_optim = os.environ.get("B200_OPTIM", "b200") != "torch"
     if own_optim:
         from unet_convlstm_b200.optim import AdamW as B200AdamW
         opt = B200AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
     else:
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=use_graph)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
     reducer = GradReducer(model.parameters()) if world > 1 else None
 
     from unet_convlstm_b200.loss import compute_loss
@@ -340,21 +388,10 @@ def run_b200_arm(args, out):
 
     # ---- fwd+bwd only (no optimizer), for the record --------------------------------------------
     ms_fb = timed(lambda: step(x_dev, y_dev, m_dev, with_opt=False), max(1, args.steps // 2))
-    # ---- timed region 1: inputs resident in HBM = the eager region above; with --graph 1 the same step --
-    #      same kernels, same order -- is captured once into a CUDA graph and replayed instead
-    #      (unet_convlstm_b200.graph.GraphedTrainStep; single GPU only) ----
-    gstep = None
-    if use_graph:
-        from unet_convlstm_b200.graph import GraphedTrainStep
-        opt.zero_grad(set_to_none=True)
-        torch.cuda.empty_cache()  # the graph keeps its own pool of activations (~60 GB at this workload)
-        gstep = GraphedTrainStep(model, opt, lambda out, y: compute_loss(torch.stack(out, dim=1), y, m_dev),
-                                 x_dev, y_dev, warmup=1)
-        for _ in range(2):
-            gstep()
-        ms_step = timed(lambda: gstep(), args.steps)
-    else:
-        ms_step = ms_eager
+    # ---- timed region 1: inputs resident in HBM = the eager region above.  (Round 1 could also replay the step from
+    #      a CUDA graph; measured 232.7 ms graphed vs 233.3 ms eager -- the step is GPU-bound, the host runs ahead --
+    #      so the graph path was removed in round 2.) ----
+    ms_step = ms_eager
 
     # ---- timed region 2: end to end through the module API, batch in pinned host memory ----------
     # Every step copies its own batch from pinned host memory (K copies inside the timed region) and reads
@@ -369,7 +406,7 @@ def run_b200_arm(args, out):
             x, y, m = pf.get()
             if i + 1 < steps:
                 pf.start(x_host, y_host, m_host)
-            (gstep(x, y) if gstep is not None else step(x, y, m)).item()
+            step(x, y, m).item()
 
     e2e_region(2)
     ms_e2e = timed(lambda: e2e_region(args.steps), 1) / args.steps
@@ -405,7 +442,7 @@ def run_b200_arm(args, out):
             "fwd_bwd_only": {"value": world * args.batch / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb},
             "eager": {"value": world * args.batch / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager,
                       "note": "same step launched kernel by kernel from Python (no CUDA graph)"},
-            "cuda_graph": use_graph,
+            "cuda_graph": False,
             "gpu_launches": launches,
             "roofline": {"kernel": "conv_tc2_kernel<256, EPI_LSTM>: fused ConvLSTM gate conv + gate math + c/h update, "
                                    "forward, CTA pairs (tcgen05 cta_group::2), one timestep-persistent launch per "
@@ -420,13 +457,13 @@ def run_b200_arm(args, out):
             "peak_mem_gb": peak_mem / 2 ** 30,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores = cpu_reference_run(args, 1, 0, args.cpu_sample)
+            v, dt, cores, kind, src = cpu_reference_run(args, 2, 1, args.cpu_sample)
             cpu_model, _ = host_info()
             line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model,
-                "sample": f"{args.cpu_sample} sequence(s), 1 training step (fwd, compute_loss, bwd, clip, AdamW) of the same model and shapes "
-                          f"(T={args.seq_len}, {args.size}x{args.size}), fp32, torch {torch.__version__} CPU "
-                          f"(oneDNN) = the reference's own ATen operators (oracle/torch_port.py), {dt:.1f} s"}
+                "value": v, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu_model, "source": src,
+                "sample": f"{args.cpu_sample} sequence(s) per step, 1 warm-up + 2 timed training steps (fwd, compute_loss, bwd, clip, AdamW) "
+                          f"of the same model and shapes (T={args.seq_len}, {args.size}x{args.size}), fp32, torch "
+                          f"{torch.__version__} CPU (oneDNN), {dt:.1f} s per step"}
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -452,11 +489,8 @@ def main():
     ap.add_argument("--size", type=int, default=64)
     ap.add_argument("--base-ch", type=int, default=64)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample", type=int, default=2, help="sequences in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="sequences in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=0,
-                    help="1: replay the step from a CUDA graph (single GPU).  Measured on B200: 232.7 ms graphed vs "
-                         "233.3 ms eager -- the step is GPU-bound, the host runs ahead -- so the default is eager")
     ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
     ap.add_argument("--timeline", default="", help="with --breakdown: write start/end/stream of every C-ABI call to this CSV")
     ap.add_argument("--profile-steps", type=int, default=0, help="run 1 warm-up + N untimed steps and exit (for ncu)")
@@ -467,7 +501,16 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, out)
     else:
-        run_b200_arm(args, out)
+        try:
+            run_b200_arm(args, out)
+        except BaseException:
+            # a device-side watchdog (csrc/ptx.cuh mbar_wait) names the barrier it timed out on
+            try:
+                from unet_convlstm_b200 import _lib
+                print(f"bench.py: b200_device_error() = {_lib.lib().b200_device_error()}", file=sys.stderr, flush=True)
+            except Exception:  # noqa: BLE001
+                pass
+            raise
     out.flush()
 
 

@@ -60,16 +60,6 @@ int b200_conv_affine_relu_tc_fwd(const void* src0, int C0, const void* src1, int
                                  const void* wpacked, const float* scale, const float* shift, int N, int ksize,
                                  void* dst, int relu, void* stream);
 
-/* The first convolution of the UNet (`inc`, unet.py:70 with 2 input channels): K = cin*9 <= 36 is too shallow for
- * the tensor-core pipeline and the layer is HBM-bound (writes N channels per pixel, reads cin), so it runs on CUDA
- * cores.  x: bf16 [IMG][H][W][Cx] (the first `cin` of the Cx channels are real); w: fp32 OIHW [N][cin][3][3];
- * y / dz: bf16 [IMG][H][W][N]; dw: fp32 OIHW [N][cin][3][3] (zeroed here, then accumulated). */
-int b200_conv_first_supported(int cin, int N);
-int b200_conv_first_fwd(const void* x, int Cx, int cin, const float* w, const float* bias, void* y, long long IMG, int H,
-                        int W, int N, void* stream);
-int b200_conv_first_wgrad(const void* dz, int N, const void* x, int Cx, int cin, long long IMG, int H, int W, float* dw,
-                          void* stream);
-
 /* nn.ConvTranspose2d(Cin, Cout, 2, stride=2) + F.pad to the skip size (Up, unet.py:90-97) in one kernel: the
  * GEMM [P, Cin] x [Cin, 4*Cout] (wpacked: bf16 [1][4*Cout (tap, co)][Cin]) whose epilogue adds bias[co] and
  * writes column block `tap` of input pixel (h, w) to output pixel (2h + tap/2 + oy, 2w + tap%2 + ox) of

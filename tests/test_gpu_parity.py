@@ -710,37 +710,6 @@ def test_inference_folded_batchnorm_matches_eval_path_and_oracle():
     assert rel2(_np(state[0][0]), ref_state[0][0].numpy()) < 2e-2
 
 
-@pytest.mark.parametrize("T,B,H,W,cin,N", [(2, 3, 16, 16, 2, 64), (1, 2, 7, 12, 2, 64), (1, 4, 64, 64, 2, 64),
-                                           (1, 2, 8, 8, 3, 128), (1, 2, 16, 16, 1, 64)])
-def test_first_layer_direct_kernels_vs_simt(T, B, H, W, cin, N):
-    """first_layer.cu (CUDA-core first conv and its weight gradient) against the generic CUDA-core kernels on the
-    zero-padded 16-channel tensor the tensor-core path would use: same bf16-rounded activations."""
-    from unet_convlstm_b200 import _lib, ops
-    g = torch.Generator(device="cuda").manual_seed(13)
-    bf = torch.bfloat16
-    x = torch.zeros(T, B, H, W, 16, device="cuda", dtype=bf)
-    x[..., :cin] = torch.randn(T, B, H, W, cin, device="cuda", generator=g).to(bf)
-    w = torch.randn(N, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5
-    bias = torch.randn(N, device="cuda", generator=g)
-    assert ops.conv_first_ok(x, None, w)
-    out = torch.full((T, B, H, W, N), float("nan"), device="cuda", dtype=bf)
-    ops.conv_first_fwd(x, w, bias, out)
-    wp = ops.pack_conv_weight(w, torch.float32, 16)          # fp32 weights: the direct kernel does not round them
-    ref = torch.empty((T, B, H, W, N), device="cuda")
-    xf = x.float()
-    st = torch.cuda.current_stream().cuda_stream
-    _lib.call("b200_conv_simt_fwd", xf.data_ptr(), 16, None, 0, T * B, H, W, wp.data_ptr(), bias.data_ptr(), N, 3,
-              ref.data_ptr(), N, N, None, 0, 1, 1, 0, st)
-    assert rel(_np(out), _np(ref)) < 6e-3                    # bf16 output rounding
-    dz = torch.randn(T, B, H, W, N, device="cuda", generator=g).to(bf)
-    dw = ops.conv_first_wgrad(dz, x, cin)
-    refw = torch.zeros(9, N, 16, device="cuda")
-    dzf = dz.float()
-    _lib.call("b200_wgrad_simt", dzf.data_ptr(), N, xf.data_ptr(), 16, T * B, H, W, 3, refw.data_ptr(), 16, 0, 1, st)
-    refw = refw[:, :, :cin].permute(1, 2, 0).reshape(N, cin, 3, 3)
-    assert rel(_np(dw), _np(refw)) < 1e-4
-
-
 class _Preset(torch.nn.Module):
     """Stand-in model of tests/golden/make_golden_metrics.py: returns preset predictions as a list of T frames."""
 

@@ -8,6 +8,7 @@ import pytest
 
 from oracle import unet_oracle as O
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 2e-6  # fixtures store gradients as fp32; everything is computed in fp64
 
 
@@ -358,3 +359,28 @@ def test_epoch_loop_batch_staging_order(monkeypatch):
     dev = [(FakeTensor(i, True), FakeTensor(i, True), FakeTensor(i, True)) for i in range(2)]
     assert [b[0].tag for b in loop._device_batches(dev, "cuda")] == [0, 1] and events == []
     assert list(loop._device_batches([], "cuda")) == []
+
+
+def test_run_reference_launcher_runs_overfit_check_unchanged_cpu(tmp_path):
+    """tools/run_reference.py on the CPU with the reference's OWN model (--impl reference): the launcher's shims (smp
+    stub, constant overrides, bounded range, synthetic NPZ) let train/overfit_check.py run as shipped."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import run_reference as RR
+        try:
+            RR.reference_root()
+        except RuntimeError:
+            pytest.skip("no copy of the reference available")
+    finally:
+        sys.path.pop(0)
+    out = tmp_path / "curve.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference.py"), "overfit", "--impl", "reference",
+                        "--iters", "1", "--seq-len", "2", "--size", "16", "--out", str(out)], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = json.loads(out.read_text())
+    assert list(res["curve"]) == ["0"] and 0 < res["curve"]["0"] < 10
+    assert "Starting Overfit Test (custom)" in r.stdout

@@ -53,7 +53,7 @@ _protos = None
 CALLS: dict = {}
 # device kernels launched per call of each entry point (memsets are not counted)
 KERNELS_PER_CALL = {
-    "b200_conv_tc_fwd": 1, "b200_conv_bnstats_tc_fwd": 1, "b200_convT2x2_tc_fwd": 1, "b200_conv_first_fwd": 1, "b200_conv_first_wgrad": 1, "b200_conv_affine_relu_tc_fwd": 1, "b200_convlstm_cell_fwd_tc": 1, "b200_convlstm_seq_fwd_tc": 1, "b200_convlstm_seq_bwd_tc": 1, "b200_wgrad_tc": 1, "b200_conv_simt_fwd": 1,
+    "b200_conv_tc_fwd": 1, "b200_conv_bnstats_tc_fwd": 1, "b200_convT2x2_tc_fwd": 1, "b200_conv_affine_relu_tc_fwd": 1, "b200_convlstm_cell_fwd_tc": 1, "b200_convlstm_seq_fwd_tc": 1, "b200_convlstm_seq_bwd_tc": 1, "b200_wgrad_tc": 1, "b200_conv_simt_fwd": 1,
     "b200_wgrad_simt": 1, "b200_bn_stats": 1, "b200_bn_finalize": 1, "b200_bn_relu_apply": 1,
     "b200_bn_relu_bwd_reduce": 1, "b200_bn_bwd_finalize": 1, "b200_bn_relu_bwd_apply": 1,
     "b200_maxpool2_fwd": 1, "b200_maxpool2_bwd": 1, "b200_lstm_gates_fwd": 1, "b200_lstm_gates_bwd": 1,

@@ -1,12 +1,13 @@
 // Host-side utilities: error reporting, device properties, TMA tensor-map encoding.
 #include "common.cuh"
 
+#include <signal.h>
 #include <stdarg.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
-#include <utility>
 
 namespace b200 {
 
@@ -33,37 +34,74 @@ int num_sms() {
     return cached[dev];
 }
 
+// pinned, device-mapped host memory (UVA: same pointer on both sides): the host can still read the barrier id
+// after a watchdog trap has killed the context -- including from the SIGABRT handler below, which is how the id
+// reaches stderr when the sticky error surfaces inside a destructor (std::terminate) rather than as an exception
+static int* g_err_flags[64] = {nullptr};
+static std::mutex g_err_mu;
+static void (*g_prev_abort)(int) = nullptr;
+
+static void abort_reporter(int sig) {
+    for (int d = 0; d < 64; ++d) {
+        int* f = g_err_flags[d];
+        if (f && *static_cast<volatile int*>(f) != 0) {
+            char buf[96];
+            int n = snprintf(buf, sizeof(buf), "b200: device %d watchdog flag = %d (see csrc/ptx.cuh mbar_wait tags)\n", d,
+                             *static_cast<volatile int*>(f));
+            if (n > 0) (void)!write(2, buf, size_t(n));
+        }
+    }
+    signal(sig, g_prev_abort ? g_prev_abort : SIG_DFL);
+    raise(sig);
+}
+
 int* device_error_flag() {
-    static int* flags[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (!g_err_flags[dev]) {
+        int* p = nullptr;
+        if (cudaHostAlloc(&p, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        *p = 0;
+        g_err_flags[dev] = p;
+        static bool installed = false;
+        if (!installed) {
+            installed = true;
+            void (*prev)(int) = signal(SIGABRT, abort_reporter);
+            g_prev_abort = (prev == SIG_ERR || prev == SIG_IGN) ? nullptr : prev;
+        }
+    }
+    return g_err_flags[dev];
+}
+
+unsigned* device_sync_counter(cudaStream_t stream) {
+    // One counter per (device, stream): two timestep-persistent kernels on different streams may run side by side.
+    // The counters of a device come from ONE pool allocated the first time the device launches such a kernel; a
+    // stream seen for the first time later only takes the next slot -- no cudaMalloc, no synchronous memset (every
+    // launch resets its counter with cudaMemsetAsync on its own stream), so a launch on a new stream is legal inside
+    // a CUDA-graph capture (the capture stream of torch.cuda.graph is never the warm-up stream).
+    constexpr int SLOTS = 256;
+    struct Pool {
+        unsigned* base = nullptr;
+        int used = 0;
+        std::map<cudaStream_t, unsigned*> by_stream;
+    };
+    static Pool pools[64];
     static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    if (!flags[dev]) {
-        // pinned, device-mapped host memory (UVA: same pointer on both sides): the host can still read
-        // the barrier id after a watchdog trap has killed the context
-        int* p = nullptr;
-        if (cudaHostAlloc(&p, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
-        *p = 0;
-        flags[dev] = p;
-    }
-    return flags[dev];
-}
-
-unsigned* device_sync_counter(cudaStream_t stream) {
-    // one counter per (device, stream): two timestep-persistent kernels on different streams may run side by side
-    static std::map<std::pair<int, cudaStream_t>, unsigned*> ctrs;
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    unsigned*& slot = ctrs[std::make_pair(dev, stream)];
-    if (!slot) {
+    Pool& pool = pools[dev];
+    auto it = pool.by_stream.find(stream);
+    if (it != pool.by_stream.end()) return it->second;
+    if (!pool.base) {
         unsigned* p = nullptr;
-        if (cudaMalloc(&p, sizeof(unsigned)) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, sizeof(unsigned));
-        slot = p;
+        if (cudaMalloc(&p, SLOTS * 32) != cudaSuccess) return nullptr;  // 32 bytes apart: one L2 sector per counter
+        pool.base = p;
     }
+    if (pool.used == SLOTS) return nullptr;
+    unsigned* slot = pool.base + 8 * pool.used++;
+    pool.by_stream[stream] = slot;
     return slot;
 }
 

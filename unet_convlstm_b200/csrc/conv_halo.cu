@@ -147,7 +147,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             int n0, img, q0, r0;
             decode(tile, n0, img, q0, r0);
             for (int c = 0; c < p.chunks; ++c) {
-                mbar_wait(aempty(sa), pa ^ 1u, p.err_flag, 100 + sa);
+                mbar_wait(aempty(sa), pa ^ 1u, p.err_flag, 3000 + 100 + sa);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(afull(sa), p.a_box_bytes);
                     const uint32_t dst = a_base + sa * p.a_stage_bytes;
@@ -163,7 +163,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                 }
                 if (!p.wres) {
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(bempty(sb), pb ^ 1u, p.err_flag, 120 + sb);
+                        mbar_wait(bempty(sb), pb ^ 1u, p.err_flag, 3000 + 120 + sb);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(bfull(sb), p.b_box_bytes);
                             tma_load_3d(b_base + sb * p.b_box_bytes, &tm_b, bfull(sb), c * p.kc, n0, tap);
@@ -189,7 +189,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
         const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_box_lo = p.b_box_bytes >> 4;
         const uint32_t row_lo = row_bytes >> 4;  // one padded position = one operand row
         if (p.wres) {
-            mbar_wait(wfull, 0, p.err_flag, 250);
+            mbar_wait(wfull, 0, p.err_flag, 3000 + 250);
             tc_fence_after();
         }
         int sa = 0, sb = 0, acc = 0;
@@ -198,12 +198,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             int n0, img, q0, r0;
             decode(tile, n0, img, q0, r0);
             const uint32_t off = q0 - r0 * p.P;  // first output position inside the loaded box
-            mbar_wait(tempty(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
+            mbar_wait(tempty(acc), acc_phase ^ 1u, p.err_flag, 3000 + 300 + acc);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             uint32_t accum = 0;
             for (int c = 0; c < p.chunks; ++c) {
-                mbar_wait(afull(sa), pa, p.err_flag, 200 + sa);
+                mbar_wait(afull(sa), pa, p.err_flag, 3000 + 200 + sa);
                 tc_fence_after();
                 const uint32_t a_row0 = a_lo0 + sa * a_stage_lo + off * row_lo;  // tap (0, 0)
                 if (p.wres) {
@@ -234,7 +234,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
                     uint32_t a_row = a_row0;
                     for (int ky = 0; ky < 3; ++ky, a_row += (p.P - 3) * row_lo) {
                         for (int kx = 0; kx < 3; ++kx, a_row += row_lo) {
-                            mbar_wait(bfull(sb), pb, p.err_flag, 220 + sb);
+                            mbar_wait(bfull(sb), pb, p.err_flag, 3000 + 220 + sb);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint64_t adesc = desc_hi | a_row;
@@ -319,7 +319,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constan
             const int w = q - h * p.P;
             const bool valid = (w < p.W) && (h < p.H);  // halo columns / rows past the image are discarded
             const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
-            mbar_wait(tfull(acc), acc_phase, p.err_flag, 400 + acc);
+            mbar_wait(tfull(acc), acc_phase, p.err_flag, 3000 + 400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BLOCK_N + half * COLS + (uint32_t(qw * 32) << 16);
 #pragma unroll 1

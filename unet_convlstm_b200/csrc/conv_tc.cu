@@ -66,7 +66,7 @@ __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, 
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if (v >= target) break;
         if (clock64() - t0 > 8000000000LL) {
-            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 900;
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 1900;
             __threadfence_system();
             asm volatile("trap;");
         }
@@ -212,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     const int cw = tc.w0 + kx - p.pad, chh = tc.h0 + ky - p.pad;
                     int kofs = 0;
                     for (int c = 0; c < chunks_t; ++c, kofs += p.kc) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
+                        mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1000 + 100 + stage);
                         if (elect_one()) {
                             const uint32_t fb = full_bar(stage);
                             mbar_arrive_expect_tx(fb, tx_bytes);
@@ -264,12 +264,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 if constexpr (EPI == EPI_LSTM_BWD) {
                     if (!tile_active(step_t(step), (tile / p.num_m_tiles) * BLOCK_N)) continue;
                 }
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 1000 + 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 uint32_t accum = 0;
                 for (int kb = 0; kb < num_kb_t; ++kb) {
-                    mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
+                    mbar_wait(full_bar(stage), phase, p.err_flag, 1000 + 200 + stage);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = desc_hi | a_lo;
@@ -381,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     }
                 }
             }
-            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 400 + acc);
+            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 1000 + 400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ void grid_wait2(const unsigned* ctr, unsigned target,
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if (v >= target) break;
         if (clock64() - t0 > 8000000000LL) {
-            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 901;
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = 2901;
             __threadfence_system();
             asm volatile("trap;");
         }
@@ -175,7 +175,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                 const int cw = tc.w0 + kx - p.pad, chh = tc.h0 + ky - p.pad;
                 int kofs = 0;
                 for (int c = 0; c < chunks_t; ++c, kofs += p.kc) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 100 + stage);
+                    mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 2000 + 100 + stage);
                     if (elect_one()) {
                         const uint32_t fb = full0_leader + 8u * stage;
                         mbar_arrive_expect_tx_cluster(fb, tx_bytes);
@@ -218,12 +218,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
             for (int step = 0; step < nsteps; ++step) {
             const int num_kb_t = (seq && step == 0 && !p.seq_have_h0) ? taps * chunks0 : num_kb;
             for (int pt = cluster_id; pt < total_ptiles; pt += num_clusters) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 300 + acc);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 2000 + 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 uint32_t accum = 0;
                 for (int kb = 0; kb < num_kb_t; ++kb) {
-                    mbar_wait(full_bar(stage), phase, p.err_flag, 200 + stage);
+                    mbar_wait(full_bar(stage), phase, p.err_flag, 2000 + 200 + stage);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = desc_hi | a_lo;
@@ -275,7 +275,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
             const bool valid = tc.in_range && (tc.h0 + hi < p.H) && (tc.b0 + bi < p.B);
             const long long pix =
                 ((static_cast<long long>(tc.t) * p.B + tc.b0 + bi) * p.H + tc.h0 + hi) * p.W + tc.w0 + wi;
-            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 400 + acc);
+            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 2000 + 400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
             if constexpr (EPI == EPI_LSTM) {

@@ -109,7 +109,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
             int b = m % p.B;
             int t = m / p.B;
             for (int rb = rb_begin; rb < rb_end; ++rb) {
-                mbar_wait(empty(stage), phase ^ 1u, p.err_flag, 500 + stage);
+                mbar_wait(empty(stage), phase ^ 1u, p.err_flag, 6000 + 500 + stage);
                 if (elect_one()) {
                     const uint32_t fb = full(stage);
                     const uint32_t dst = smem_base + stage * stage_bytes;
@@ -152,11 +152,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
             const int split = unit / p.s_tiles;
             const int rb_begin = split * p.rb_per_split;
             const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-            mbar_wait(tempty, pt ^ 1u, p.err_flag, 700);
+            mbar_wait(tempty, pt ^ 1u, p.err_flag, 6000 + 700);
             tc_fence_after();
             uint32_t accum = 0;
             for (int rb = rb_begin; rb < rb_end; ++rb) {
-                mbar_wait(full(stage), phase, p.err_flag, 600 + stage);
+                mbar_wait(full(stage), phase, p.err_flag, 6000 + 600 + stage);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t src_lo = smem_lo + stage * (stage_bytes >> 4);
@@ -210,7 +210,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
             const int split = unit / p.s_tiles;
             const int s0 = (unit - split * p.s_tiles) * 64;
-            mbar_wait(tfull, pt, p.err_flag, 800);
+            mbar_wait(tfull, pt, p.err_flag, 6000 + 800);
             pt ^= 1u;
             tc_fence_after();
             for (int g = 0; g < ngroups; ++g) {

@@ -173,6 +173,10 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
         const int pid = warp == 0 ? 0 : (warp < 8 ? warp - 1 : warp - 5);
         constexpr int MAX_GU = Cfg::MAX_GU;
         const uint32_t vfull0_l = map_to_cta(vfull(0), 0), sfull0_l = map_to_cta(sfull(0), 0);
+        int turn = 0;  // producer that fills the next ring position
+        // at most SV warps take turns (the parity argument at the vempty wait needs SV >= the number of warps dealt to);
+        // with a shorter ring the remaining producer warps own nothing and never touch a barrier
+        constexpr int NTURN = SV < NPROD ? SV : NPROD;
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0;
         for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
@@ -202,7 +206,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
             for (int rb = rb_begin; rb < rb_end; ++rb) {
                 const int w0 = wt * p.Wt, h0 = ht * p.Ht, b0 = bt * p.Bt;
                 if (pid == 0) {
-                    mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 500 + ss);
+                    mbar_wait(sempty(ss), ps ^ 1u, p.err_flag, 5000 + 500 + ss);
                     if (elect_one()) {
                         const uint32_t fb = sfull0_l + 8u * ss;
                         mbar_arrive_expect_tx_cluster(fb, s_tx);
@@ -220,9 +224,17 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
 #pragma unroll
                 for (int g = 0; g < MAX_GU; ++g) {
                     if (g < u.ngr) {
-                        // every producer waits for every stage (a parity wait is only valid within one lap)
-                        mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 520 + sv);
-                        if (g % NPROD == pid) {
+                        // The stages of the ring are dealt to NTURN producer warps ROUND-ROBIN OVER THE RING POSITION (`turn`),
+                        // not over the group index g as in round 1, and a producer waits only for the stages it fills.
+                        // A parity wait on vempty(sv) is unambiguous iff the waiter is neither a lap behind nor a lap
+                        // ahead of the barrier.  The owner of position q (lap L) cannot be behind: completion L + 1 of
+                        // that stage needs ITS fill.  It cannot be ahead: it filled position q - NTURN after the MMA
+                        // warp consumed q - NTURN - SV >= q - 2 SV (NTURN <= SV), i.e. at least L - 1 completions.
+                        // Round 1 dealt by g and made every producer wait on every stage: in units with fewer groups
+                        // than producers a warp owned nothing, nothing held it, it fell a lap behind, its parity
+                        // aliased and the kernel hung (watchdog 4523 / 4800, profiles/r02_fault_root_cause.md).
+                        if (turn == pid) {
+                            mbar_wait(vempty(sv), pv ^ 1u, p.err_flag, 5000 + 520 + sv);
                             if (elect_one()) {
                                 const uint32_t fb = vfull0_l + 8u * sv;
                                 mbar_arrive_expect_tx_cluster(fb, v_tx);
@@ -248,6 +260,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
                             }
                             __syncwarp();
                         }
+                        if (++turn == NTURN) turn = 0;
                         if (++sv == SV) {
                             sv = 0;
                             pv ^= 1u;
@@ -282,15 +295,15 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
                 const Wg2Unit u = wg2_decode<BLOCK_N, STACKED>(p, unit);
                 const int rb_begin = u.split * p.rb_per_split;
                 const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
-                mbar_wait(tempty, pt ^ 1u, p.err_flag, 700);
+                mbar_wait(tempty, pt ^ 1u, p.err_flag, 5000 + 700);
                 tc_fence_after();
                 uint32_t accum = 0;
                 for (int rb = rb_begin; rb < rb_end; ++rb) {
-                    mbar_wait(sfull(ss), ps, p.err_flag, 600 + ss);
+                    mbar_wait(sfull(ss), ps, p.err_flag, 5000 + 600 + ss);
                     const uint32_t s_lo = s_lo0 + ss * (Cfg::S_BYTES >> 4);
                     uint32_t d_tmem = tmem_base;
                     for (int g = 0; g < u.ngr; ++g, d_tmem += BLOCK_N) {
-                        mbar_wait(vfull(sv), pv, p.err_flag, 620 + sv);
+                        mbar_wait(vfull(sv), pv, p.err_flag, 5000 + 620 + sv);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t v_lo = v_lo0 + sv * (Cfg::V_BYTES >> 4);
@@ -330,7 +343,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
         for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
             const Wg2Unit u = wg2_decode<BLOCK_N, STACKED>(p, unit);
             const int ncols = STACKED ? min(BLOCK_N, p.Nz - u.s0) : min(BLOCK_N, p.Csrc - u.v0);
-            mbar_wait(tfull, pt, p.err_flag, 800);
+            mbar_wait(tfull, pt, p.err_flag, 5000 + 800);
             pt ^= 1u;
             tc_fence_after();
             for (int g = 0; g < u.ngr; ++g) {

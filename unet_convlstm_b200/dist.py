@@ -33,6 +33,7 @@ class GradReducer:
             self._add_bucket(cur)
         self._pending = [0] * len(self.buckets)
         self._works = []
+        ops.enable_background_wgrad()  # _on_grad below orders its reads after the background stream
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         for p in self.params:
             p._b200_bg_aware = True  # _on_grad orders its reads after the background stream (ops.background)

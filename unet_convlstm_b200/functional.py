@@ -120,16 +120,6 @@ class ConvBnRelu(torch.autograd.Function):
         if K > C0 + C1 or (x1 is not None and K != C0 + C1):
             raise ValueError(f"conv weight expects {K} input channels, got {C0}+{C1}")
         z = torch.empty((T, B, H, W, N), device=x0.device, dtype=dt)
-        first = ops.FIRST_LAYER_DIRECT and ops.conv_first_ok(x0, x1, weight)
-        if first:
-            # the UNet's first conv (K = 2*9): HBM-bound, CUDA-core kernel on the un-padded weights
-            ops.conv_first_fwd(x0, weight, bias.detach() if bias is not None else None, z)
-            y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum)
-            ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
-            ctx.tstride = stats[4]
-            ctx.training, ctx.cache, ctx.has_bias, ctx.first = training, cache, bias is not None, True
-            return y
-        ctx.first = False
         wp = cache.get(("fwd", dt, C0 + C1), (weight,), lambda: ops.pack_conv_weight(weight, dt, C0 + C1))
         # The BatchNorm sums CAN come out of the conv epilogue (b200_conv_bnstats_tc_fwd), but measured on
         # B200 the cross-lane column reduction makes the epilogue of the narrow layers longer than their
@@ -161,8 +151,6 @@ class ConvBnRelu(torch.autograd.Function):
                                                    ctx.has_bias)
         # weight gradient, batched over all T*B images
         def wgrad():
-            if ctx.first:
-                return ops.conv_first_wgrad(dz, x0, K)
             dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
             ops.conv_wgrad(dz, x0, ks, dwp, 0)
             if x1 is not None:

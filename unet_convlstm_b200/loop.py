@@ -107,6 +107,8 @@ def train_one_epoch(model, loader, optimizer, device, dataset_obj, use_mask=True
     """One epoch of main.py:77-145: forward, compute_loss, backward, clip_grad_norm_(max_norm), optimizer step, and
     the running loss / MAE / RMSE / ME.  `after_backward`: optional callable run between backward and the clip
     (the data-parallel gradient reducer's `finish`)."""
+    from . import ops
+    ops.enable_background_wgrad()  # gradients are read after backward() (clip + optimizer below, or the GradReducer)
     model.train()
     device = torch.device(device)
     metrics = RunningMetrics(dataset_obj, device)

@@ -250,32 +250,6 @@ def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False, bn_ws=None):
     return False
 
 
-def conv_first_ok(x0, x1, weight) -> bool:
-    """The UNet's first convolution (2 input channels zero-padded to one K chunk): CUDA-core kernels."""
-    return (x1 is None and x0.dtype == torch.bfloat16 and weight.shape[2] == 3 and weight.shape[3] == 3
-            and weight.shape[1] < 16 and weight.shape[0] % 64 == 0
-            and _lib.supported("b200_conv_first_supported", weight.shape[1], weight.shape[0]))
-
-
-def conv_first_fwd(x0, weight, bias, out):
-    _chk(x0, "x0"), _chk(out, "out")
-    T, B, H, W, Cx = x0.shape
-    N, cin = weight.shape[0], weight.shape[1]
-    w = weight.detach().float().contiguous()
-    _lib.call("b200_conv_first_fwd", _p(x0), Cx, cin, _p(w), _p(bias), _p(out), T * B, H, W, N, _st(),
-              tag=f"cin{cin} N{N} {H}x{W} first", work=(None, (x0.numel() + out.numel()) * 2))
-    return out
-
-
-def conv_first_wgrad(dz, x0, cin):
-    _chk(dz, "dz"), _chk(x0, "x0")
-    T, B, H, W, N = dz.shape
-    dw = torch.empty((N, cin, 3, 3), device=dz.device, dtype=torch.float32)
-    _lib.call("b200_conv_first_wgrad", _p(dz), N, _p(x0), x0.shape[-1], cin, T * B, H, W, _p(dw), _st(),
-              tag=f"cin{cin} N{N} {H}x{W} first", work=(None, (x0.numel() + dz.numel()) * 2))
-    return dw
-
-
 def conv_affine_relu_ok(x0, x1, N) -> bool:
     return x0.dtype == torch.bfloat16 and tc_conv_ok(x0, x1, N)
 
@@ -487,11 +461,6 @@ def lstm_tc_ok(x_t, Ch) -> bool:
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
 
-# First UNet convolution (2 input channels): zero-padded to 16 channels on the tensor-core path (0, default) or the
-# CUDA-core kernels of first_layer.cu (1).  Measured in the cfg-2 step: tensor-core 3.8 ms fwd + 2.4 ms wgrad, the
-# straightforward CUDA-core kernels 8.1 + 15.6 ms -- kept opt-in with their parity test, not used.
-FIRST_LAYER_DIRECT = os.environ.get("B200_FIRST_LAYER_DIRECT", "0") == "1"
-
 # ConvTranspose 2x2: pixel shuffle in the GEMM epilogue (1) or GEMM + separate shuffle kernel (0)
 CONVT_FUSED = os.environ.get("B200_CONVT_FUSED", "1") != "0"
 
@@ -511,7 +480,28 @@ FUSED_BPTT = os.environ.get("B200_FUSED_BPTT", "0") == "1"
 # sums / apply, gate gradients, pooling) leave the tensor pipes idle.  With the wgrad kernels queued on a second
 # stream their CTAs share the SMs with those pointwise blocks (a persistent wgrad CTA leaves ~40 K registers and room
 # for two 256-thread blocks per SM).  The current stream re-joins the background stream when backward ends.
-WGRAD_STREAM = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
+#
+# OPT-IN: a gradient produced on the background stream is only safe if nothing reads it on the current
+# stream before backward ends.  _leaf_takes_gradient_as_is() sees tensor hooks and post-accumulate hooks, but hooks on
+# the AccumulateGrad NODE -- how torch DistributedDataParallel / FSDP attach their reducers -- cannot be listed from
+# Python, so a DDP-wrapped model would copy a gradient that is still being written.  The switch is therefore off
+# unless a component that KNOWS the ordering turns it on: this package's GradReducer (dist.py), its training loop
+# (loop.py), bench.py and tools/soak.py call enable_background_wgrad(); B200_WGRAD_STREAM=1 / 0 forces it on / off.
+_WGRAD_STREAM_ENV = os.environ.get("B200_WGRAD_STREAM", "")
+WGRAD_STREAM = _WGRAD_STREAM_ENV == "1"
+
+
+def enable_background_wgrad(on: bool = True) -> bool:
+    """Turns the background weight-gradient stream on (or off) for this process, unless B200_WGRAD_STREAM forces a
+    value.  Call it only from a training step that reads parameter gradients AFTER backward() has returned (plain
+    optimizers, this package's GradReducer); leave it off under torch DistributedDataParallel / FSDP."""
+    global WGRAD_STREAM
+    if _WGRAD_STREAM_ENV in ("0", "1"):
+        return WGRAD_STREAM
+    WGRAD_STREAM = bool(on)
+    return WGRAD_STREAM
+
+
 _BG_DEBUG_DELAY = int(os.environ.get("B200_WGRAD_STREAM_DEBUG_DELAY", "0"))  # spin cycles before every background block (tests)
 # ConvLSTM BPTT: timesteps per weight-gradient chunk queued on the background stream while the sweep continues
 # (0 = one weight-gradient reduction after the sweep, the default).  Measured (profiles/r01_background_wgrad_ab.txt):
@@ -561,6 +551,7 @@ class background:
 
     def __init__(self, grad_target, *inputs, allow=True):
         self.inputs = [t for t in inputs if t is not None]
+        self.targets = list(grad_target) if isinstance(grad_target, (tuple, list)) else [grad_target]
         task = torch._C._current_graph_task_id()
         self.active = bool(WGRAD_STREAM and allow and task != -1 and not torch.is_grad_enabled()
                            and all(_leaf_takes_gradient_as_is(p) for p in
@@ -593,17 +584,35 @@ class background:
         return False
 
     def keep(self, *tensors):
-        """Tensors created inside the block that the CURRENT stream will own afterwards (returned gradients)."""
+        """Tensors created inside the block that the CURRENT stream will own afterwards (returned gradients, in the
+        order of the block's parameters)."""
         if self.active:
             cur = torch.cuda.current_stream()
             for t in tensors:
                 if t is not None:
                     t.record_stream(cur)
+            for p, t in zip(self.targets, tensors):
+                if p is not None and t is not None and tuple(t.shape) == tuple(p.shape):
+                    _bg_delivered.append((p, t.data_ptr()))
+
+
+# (parameter, data_ptr of the gradient produced on the background stream) of the running backward pass
+_bg_delivered: list = []
 
 
 def _end_of_backward_join():
     _bg_joined_task[0] = -1
     background_join()
+    # AccumulateGrad must have STORED each background gradient (same storage).  Had it cloned or accumulated instead
+    # (a second reference to the gradient, mismatching strides, a .grad that appeared meanwhile), that kernel ran on
+    # the current stream while the background stream was still writing: corrupt, so fail loudly.
+    delivered, _bg_delivered[:] = list(_bg_delivered), []
+    for p, ptr in delivered:
+        g = p.grad
+        if g is not None and g.data_ptr() != ptr and not getattr(p, "_b200_bg_aware", False):
+            raise RuntimeError("background weight-gradient stream: autograd did not store the gradient of a parameter as "
+                               "produced (it was copied or accumulated during backward, on the current stream, while the "
+                               "background stream was still writing it).  Call ops.enable_background_wgrad(False).")
 
 
 # bench.py sets this to a list to time every fused cell launch with CUDA events on the launching stream:
