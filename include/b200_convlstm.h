@@ -32,6 +32,9 @@ const char* b200_last_error(void);
 /* Reads and clears the device watchdog flag (non-zero: id of the mbarrier a kernel timed out on). */
 int b200_device_error(void);
 
+/* TMA tensor maps are cached per (base pointer, dims, strides, box) inside the library: counters since load. */
+int b200_tmap_cache_stats(long long* hits, long long* misses);
+
 /* 1 if the tcgen05 path can tile this problem (else use the *_simt entry points). */
 int b200_conv_tc_supported(int B, int H, int W, int C0, int C1, int N, int lstm);
 
@@ -80,11 +83,22 @@ int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_prev, int Ch
  * (L2-resident) state buffers, a grid-wide counter separates the steps, no host round trip per step.
  * x_seq: bf16 [T][B][H][W][Cin]; h_all: bf16 [T+1][B][H][W][Ch], slot 0 = initial state (ignored when
  * have_h0 == 0: zero state, unet.py:23-25), slot t+1 = h_t; c_all: fp32 [T+1][...] likewise;
- * gates: bf16 [T][P][4][Ch] activated i,f,g,o (kept for BPTT).  Also uses one 4-byte per-device step
+ * gates: bf16 [T][P][4][Ch] activated i,f,g,o (kept for BPTT), or NULL (gate recompute, see
+ * b200_convlstm_gates_recompute_tc).  Also uses one 4-byte per-device step
  * counter owned by the library. */
 int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all, int Ch, int T, int B, int H, int W,
                              const void* wpacked, const float* bias_packed, float* c_all, void* gates,
                              int have_h0, int ksize, void* stream);
+
+/* Gate recompute for BPTT (north_star "gate-gradient recompute"; the reference's autograd instead keeps the four
+ * activated gates of every step, unet.py:29-33): the activated gates of ALL T steps from the stored x_t, h_{t-1}
+ * (h_all slot t) and c_{t-1} (c_all slot t) in one tensor-core launch -- the steps are independent once the states
+ * are known.  Same arithmetic as the forward kernel; writes only gates_out (bf16 [T][P][4][Ch]), which may be the
+ * buffer the gate-gradient kernel then overwrites with dz.  With a zero initial state slot 0 of h_all / c_all must
+ * hold zeros. */
+int b200_convlstm_gates_recompute_tc(const void* x_seq, int Cin, const void* h_all, int Ch, int T, int B, int H, int W,
+                                     const void* wpacked, const float* bias_packed, const float* c_all, void* gates_out,
+                                     int ksize, void* stream);
 
 /* Whole-sequence BPTT data path of one ConvLSTM layer -- the autograd of the t-loop of ConvLSTM.forward
  * (unet.py:52-57) -- as ONE timestep-persistent cooperative kernel running t = T-1 .. 0.  Step t is the

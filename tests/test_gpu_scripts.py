@@ -33,21 +33,28 @@ def reference_curve():
     return {int(k): v for k, v in res["curve"].items()}
 
 
-@pytest.mark.parametrize("precision,tol0,tol", [("fp32", 1e-4, 0.25), ("bf16", 2e-2, 0.35)])
-def test_overfit_check_loss_curve_matches_reference(reference_curve, precision, tol0, tol):
-    """overfit_check.run_overfit_test_and_save (overfit_check.py:36-139): masked-MSE loss printed at iterations
-    0, 100, 200, 300 of AdamW on 16 sequences, base_ch 64 + skip ConvLSTMs.  Iteration 0 is a pure forward pass and
-    must agree to the mode's tolerance; later points sit on a chaotic optimisation trajectory (the reference run with
-    and without TF32 differs by ~10-20 % there), so they are held to a relative band, and both runs must have
-    reduced the loss by the same order of magnitude."""
-    res, _ = _run("overfit", "--impl", "b200", "--precision", precision, "--iters", "300")
+SUCCESS = 5e-4   # the script's own convergence criterion (overfit_check.py:116)
+
+
+@pytest.mark.parametrize("precision,tol0", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_overfit_check_loss_curve_matches_reference(reference_curve, precision, tol0):
+    """overfit_check.run_overfit_test_and_save (overfit_check.py:36-139): masked-MSE loss printed every 100 iterations
+    of AdamW on 16 sequences, base_ch 64 + skip ConvLSTMs, until the script's own success criterion (loss < 5e-4) stops
+    it.  Iteration 0 is a pure forward pass and must agree to the mode's tolerance.  Iteration 100 must agree within
+    35 %.  Beyond that the trajectory is chaotic in the reference itself -- measured on B200 (profiles/
+    r02_overfit_curves.txt): reference fp32 0.000631 / 0.001037 / 0.000121 at 100 / 200 / 300, reference with cuDNN
+    TF32 0.000534 / 0.000200 (stops at 200) -- so later points are held to "no worse than twice the reference, or
+    already below the success threshold", and the run must reach the script's [SUCCESS] branch within 300 iterations."""
+    res, out = _run("overfit", "--impl", "b200", "--precision", precision, "--iters", "300")
     assert res["unet_module"] == os.path.join(ROOT, "train", "unet.py")
     curve = {int(k): v for k, v in res["curve"].items()}
-    assert sorted(curve) == sorted(reference_curve) == [0, 100, 200, 300]
     assert abs(curve[0] - reference_curve[0]) <= tol0 * reference_curve[0], (curve, reference_curve)
-    for it in (100, 200, 300):
-        assert abs(curve[it] - reference_curve[it]) <= tol * reference_curve[it] + 2e-4, (it, curve, reference_curve)
-    assert curve[300] < 0.2 * curve[0]
+    assert abs(curve[100] - reference_curve[100]) <= 0.35 * reference_curve[100], (curve, reference_curve)
+    for it, v in curve.items():
+        if it >= 200 and it in reference_curve:
+            assert v <= max(2 * reference_curve[it], SUCCESS), (it, curve, reference_curve)
+    assert "[SUCCESS]" in out and min(curve.values()) < SUCCESS, curve
+    assert min(reference_curve.values()) < SUCCESS, reference_curve
 
 
 def test_main_and_get_metrics_run_unchanged():

@@ -217,7 +217,10 @@ def _seed(seed):
 
 
 def _work_dir():
-    d = os.path.join(ROOT, "gpurun_out", "run_reference")
+    """Scratch directory for the synthetic NPZ and the checkpoints the scripts save (0.5 GB each at base_ch 64):
+    outside the repository, so they neither enter a snapshot nor gpurun_out/."""
+    import tempfile
+    d = os.environ.get("B200_WORK_DIR") or os.path.join(tempfile.gettempdir(), "b200_run_reference")
     os.makedirs(d, exist_ok=True)
     return d
 

@@ -91,14 +91,60 @@ def last_error() -> str:
 TIMER = None
 
 
+# ------------------------------------------------------------------------------------------------
+# Binding.  "torch" (default): the TORCH_LIBRARY(b200convlstm, ...) custom ops of libb200convlstm_torch.so
+# (csrc/torch_ops.cpp, generated from the header): tensors in, launch on torch's current stream, TORCH_CHECK -> RuntimeError.
+# "ctypes": the C ABI called directly.  A call whose pointer arguments are raw addresses or host arrays (tests, the
+# strided-copy and multi-tensor entry points) always takes the ctypes route.
+# ------------------------------------------------------------------------------------------------
+BINDING = os.environ.get("B200_BINDING", "torch")
+TORCH_LIB_PATH = os.path.join(HERE, "libb200convlstm_torch.so")
+_torch_ops = None     # {entry point: (op, number of pointer-typed parameters mask)}
+TORCH_OP_CALLS = [0]  # calls that went through torch.ops.b200convlstm (tests)
+
+
+def torch_ops():
+    """{name: (torch op, [is_pointer per C parameter, without the trailing stream])}; loads the op library once."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        lib()
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise RuntimeError(f"{TORCH_LIB_PATH} not found: build it with `python -m unet_convlstm_b200.build` "
+                               "(or set B200_BINDING=ctypes to call the C ABI directly)")
+        torch.ops.load_library(TORCH_LIB_PATH)
+        ops = {}
+        for name, (_, argtypes) in _protos.items():
+            short = name[len("b200_"):]
+            if argtypes and argtypes[-1] is ctypes.c_void_p and hasattr(torch.ops.b200convlstm, short):
+                ops[name] = (getattr(torch.ops.b200convlstm, short), [a is ctypes.c_void_p for a in argtypes[:-1]])
+        _torch_ops = ops
+    return _torch_ops
+
+
+def _is_tensor(a) -> bool:
+    return hasattr(a, "data_ptr")
+
+
 def call(name: str, *args, tag: str = "", work=None):
-    """Calls an int-returning entry point and raises on a non-zero status."""
+    """Calls an int-returning entry point and raises on a non-zero status.  Pointer arguments may be tensors (or None)."""
     timer = TIMER
     if timer is not None:
         import torch
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = getattr(lib(), name)(*args)
+    op = None
+    if BINDING == "torch":
+        ent = torch_ops().get(name)
+        if ent is not None and len(ent[1]) == len(args) - 1 and any(_is_tensor(a) for a in args) and all(
+                (a is None or _is_tensor(a)) if isptr else not _is_tensor(a) for a, isptr in zip(args, ent[1])):
+            op = ent[0]
+    if op is not None:
+        op(*args[:-1])      # the op takes torch's current stream itself and raises on a non-zero status
+        TORCH_OP_CALLS[0] += 1
+        rc = 0
+    else:
+        rc = getattr(lib(), name)(*[a.data_ptr() if _is_tensor(a) else a for a in args])
     if timer is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()

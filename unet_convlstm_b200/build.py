@@ -15,6 +15,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200convlstm.so")
+# the torch custom-op face of the C ABI: csrc/torch_ops.cpp (generated from the header by tools/gen_torch_ops.py),
+# compiled with the host compiler against torch's headers and linked to LIB
+TORCH_LIB = os.path.join(HERE, "libb200convlstm_torch.so")
+TORCH_SRC = os.path.join(CSRC, "torch_ops.cpp")
+CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # no --use_fast_math: the fp32 check mode needs IEEE tanhf/expf/division; the bf16 kernels ask for
 # tanh.approx explicitly where they want it
@@ -57,7 +62,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_torch_ops(force)
     return LIB
+
+
+def build_torch_ops(force: bool = False) -> str:
+    """g++ -shared csrc/torch_ops.cpp -> libb200convlstm_torch.so (TORCH_LIBRARY(b200convlstm, ...) registrations)."""
+    deps = [TORCH_SRC, os.path.join(os.path.dirname(HERE), "include", "b200_convlstm.h"), LIB]
+    if not force and os.path.exists(TORCH_LIB) and os.path.getmtime(TORCH_LIB) >= _newest(deps):
+        return TORCH_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch.compiled_with_cxx11_abi())}",
+           *[f"-I{d}" for d in ce.include_paths()], f"-I{cuda_inc}", TORCH_SRC, "-o", TORCH_LIB,
+           f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda",
+           f"-L{HERE}", "-lb200convlstm", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("building libb200convlstm_torch.so failed")
+    return TORCH_LIB
 
 
 if __name__ == "__main__":

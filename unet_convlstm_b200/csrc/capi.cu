@@ -31,6 +31,14 @@ extern "C" int b200_device_error(void) {
     return v;
 }
 
+extern "C" int b200_tmap_cache_stats(long long* hits, long long* misses) {
+    unsigned long long h = 0, m = 0;
+    tmap_cache_stats(&h, &m);
+    if (hits) *hits = static_cast<long long>(h);
+    if (misses) *misses = static_cast<long long>(m);
+    return B200_OK;
+}
+
 extern "C" int b200_conv_tc_supported(int B, int H, int W, int C0, int C1, int N, int lstm) {
     MTile mt;
     if (!plan_mtile(B, H, W, 128, &mt)) return 0;
@@ -177,7 +185,7 @@ extern "C" int b200_convlstm_cell_fwd_tc(const void* x, int Cin, const void* h_p
 extern "C" int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all, int Ch, int T, int B, int H, int W,
                                         const void* wpacked, const float* bias_packed, float* c_all, void* gates,
                                         int have_h0, int ksize, void* stream) {
-    if (!x_seq || !h_all || !wpacked || !c_all || !gates || Ch <= 0 || Cin <= 0 || T <= 0) {
+    if (!x_seq || !h_all || !wpacked || !c_all || Ch <= 0 || Cin <= 0 || T <= 0) {
         set_last_error("b200_convlstm_seq_fwd_tc: bad arguments");
         return B200_ERR_ARG;
     }
@@ -201,6 +209,27 @@ extern "C" int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all,
     }();
     if (pair_mode > 0) return launch_conv_tc2(x_seq, h_all, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
     return launch_convlstm_seq_tc(x_seq, h_all, wpacked, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_convlstm_gates_recompute_tc(const void* x_seq, int Cin, const void* h_all, int Ch, int T, int B, int H,
+                                                int W, const void* wpacked, const float* bias_packed, const float* c_all,
+                                                void* gates_out, int ksize, void* stream) {
+    if (!x_seq || !h_all || !wpacked || !c_all || !gates_out || Ch <= 0 || Cin <= 0 || T <= 0) {
+        set_last_error("b200_convlstm_gates_recompute_tc: bad arguments");
+        return B200_ERR_ARG;
+    }
+    // all T steps at once: with h_{t-1} and c_{t-1} stored, the gate pre-activations of different steps are independent
+    ConvTcParams p = {};
+    p.T = T; p.B = B; p.H = H; p.W = W;
+    p.C0 = Cin; p.C1 = Ch;
+    p.N = 4 * Ch; p.ksize = ksize;
+    p.wK = Cin + Ch;
+    p.bias = bias_packed;
+    p.c_prev = c_all;            // slot t = c_{t-1}
+    p.c_next = nullptr;          // state outputs are not rewritten
+    p.h_next = nullptr;
+    p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
+    return launch_conv_tc2(x_seq, h_all, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_convlstm_seq_bwd_tc(void* dz_all, const void* wd_packed, const void* gates, const float* c_all,

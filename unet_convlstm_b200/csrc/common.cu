@@ -3,6 +3,7 @@
 
 #include <signal.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -134,6 +135,63 @@ static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Tensor-map cache ("TMA descriptors cached per (ptr, shape)").  A training step encodes the
+// same ~300 maps again every step (the caching allocator hands out the same addresses); the 128-byte CUtensorMap is a
+// pure function of (base, dims, strides, box), so a direct-mapped table keyed by those replaces the driver call by one
+// compare.  Collisions simply re-encode.
+// ----------------------------------------------------------------------------------------------
+struct TmapKey {
+    const void* base;
+    uint64_t d[5];
+    uint64_t s[4];
+    uint32_t b[5];
+    uint32_t rank;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+    TmapKey key;
+    CUtensorMap map;
+    bool used;
+};
+static constexpr int TMAP_SLOTS = 2048;
+static TmapSlot* g_tmap_cache = nullptr;
+static std::mutex g_tmap_mu;
+static unsigned long long g_tmap_hits = 0, g_tmap_misses = 0;
+
+static uint64_t tmap_hash(const TmapKey& k) {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h ^ (h >> 29);
+}
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (!g_tmap_cache) g_tmap_cache = static_cast<TmapSlot*>(calloc(TMAP_SLOTS, sizeof(TmapSlot)));
+    if (!g_tmap_cache) return false;
+    TmapSlot& sl = g_tmap_cache[tmap_hash(k) % TMAP_SLOTS];
+    if (sl.used && sl.key == k) {
+        *out = sl.map;
+        ++g_tmap_hits;
+        return true;
+    }
+    ++g_tmap_misses;
+    return false;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (!g_tmap_cache) return;
+    TmapSlot& sl = g_tmap_cache[tmap_hash(k) % TMAP_SLOTS];
+    sl.key = k;
+    sl.map = m;
+    sl.used = true;
+}
+void tmap_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    *hits = g_tmap_hits;
+    *misses = g_tmap_misses;
+}
+
 int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
                  const uint64_t strides_elems[4], const uint32_t box[5]) {
     EncodeTiledFn fn = get_encode_fn();
@@ -145,6 +203,13 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
         set_last_error("TMA base pointer %p not 16-byte aligned", base);
         return B200_ERR_ALIGN;
     }
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base;
+    key.rank = 5;
+    for (int i = 0; i < 5; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+    for (int i = 0; i < 4; ++i) key.s[i] = strides_elems[i];
+    if (tmap_lookup(key, out)) return B200_OK;
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bx[5], estr[5];
     for (int i = 0; i < 5; ++i) {
@@ -171,6 +236,7 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
             bx[0], bx[1], bx[2], bx[3], bx[4]);
         return B200_ERR_CUDA;
     }
+    tmap_store(key, *out);
     return B200_OK;
 }
 
@@ -193,6 +259,13 @@ int make_w_tmap(CUtensorMap* out, const void* base, int K, int rows, int taps, i
         set_last_error("weight TMA map: base %p / K=%d misaligned", base, K);
         return B200_ERR_ALIGN;
     }
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base;
+    key.rank = 3;
+    key.d[0] = uint64_t(K); key.d[1] = uint64_t(rows); key.d[2] = uint64_t(taps);
+    key.b[0] = uint32_t(box_k); key.b[1] = uint32_t(box_rows); key.b[2] = 1;
+    if (tmap_lookup(key, out)) return B200_OK;
     cuuint64_t gdim[3] = {cuuint64_t(K), cuuint64_t(rows), cuuint64_t(taps)};
     cuuint64_t gstr[2] = {cuuint64_t(K) * 2, cuuint64_t(K) * 2 * rows};
     cuuint32_t bx[3] = {cuuint32_t(box_k), cuuint32_t(box_rows), 1u};
@@ -205,6 +278,7 @@ int make_w_tmap(CUtensorMap* out, const void* base, int K, int rows, int taps, i
                        int(r), K, rows, taps, box_k, box_rows);
         return B200_ERR_CUDA;
     }
+    tmap_store(key, *out);
     return B200_OK;
 }
 

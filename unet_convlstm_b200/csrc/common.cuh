@@ -56,6 +56,9 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
 int make_w_tmap(CUtensorMap* out, const void* base, int K, int rows, int taps, int box_k,
                 int box_rows);
 
+// hits / misses of the tensor-map cache since the library was loaded
+void tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);
+
 // M-tile geometry: 128 output pixels = Wt x Ht x Bt box (w fastest).  Returns false if the
 // spatial shape cannot be tiled by the tensor-core path.
 struct MTile {

@@ -616,15 +616,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                             cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
                             hn[j] = go[j] * fast_tanh(cn[j]);
                         }
-                        float4* co = reinterpret_cast<float4*>(p.c_next + coff);
+                        if (p.c_next) {
+                            float4* co = reinterpret_cast<float4*>(p.c_next + coff);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            co[j] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
-                        uint4* ho = reinterpret_cast<uint4*>(p.h_next + coff);
-                        ho[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
-                                           pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
-                        ho[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]),
-                                           pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
+                            for (int j = 0; j < 4; ++j)
+                                co[j] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+                        }
+                        if (p.h_next) {
+                            uint4* ho = reinterpret_cast<uint4*>(p.h_next + coff);
+                            ho[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                               pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+                            ho[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]),
+                                               pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15]));
+                        }
                         if (p.gates_out) {
                             __nv_bfloat16* gb = p.gates_out + pix * (4LL * Ch) + ch;
                             auto st16 = [](__nv_bfloat16* dst, const float* s) {

@@ -334,9 +334,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                     // Ch is a multiple of 16 and the state buffers come from the caching allocator (512-byte
                     // aligned): every 16-channel piece is 32-byte aligned -> 256-bit stores
                     auto st16 = [](__nv_bfloat16* dst, const float* sv) { st_bf16x16(dst, sv); };
-                    st_f32x8(p.c_next + coff, cn);
-                    st_f32x8(p.c_next + coff + 8, cn + 8);
-                    st16(p.h_next + coff, hn);
+                    // c_next / h_next are NULL in the gate-recompute pass of BPTT (b200_convlstm_gates_recompute_tc)
+                    if (p.c_next) {
+                        st_f32x8(p.c_next + coff, cn);
+                        st_f32x8(p.c_next + coff + 8, cn + 8);
+                    }
+                    if (p.h_next) st16(p.h_next + coff, hn);
                     if (p.gates_out) {
                         __nv_bfloat16* gb = p.gates_out + pix * (4LL * Ch) + ch;
                         st16(gb, gi);

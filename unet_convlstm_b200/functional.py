@@ -320,13 +320,16 @@ class ConvLSTMSeq(torch.autograd.Function):
         fused = ops.lstm_tc_ok(x_seq[0], Ch)
         h_all = torch.empty((T + 1, B, H, W, Ch), device=dev, dtype=dt)
         c_all = torch.empty((T + 1, B, H, W, Ch), device=dev, dtype=torch.float32)
-        gates = torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
+        # gate recompute (ops.GATE_RECOMPUTE): the activated gates are not kept for backward
+        recompute = bool(fused and ops.GATE_RECOMPUTE and any(ctx.needs_input_grad))
+        gates = None if recompute else torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
         have_h0 = h0 is not None
         if have_h0:
             ops.copy_(h_all[0], h0.detach())
             ops.copy_(c_all[0], c0.detach())
-        elif not fused:
-            h_all[0].zero_()
+        elif not fused or recompute:
+            h_all[0].zero_()      # the recompute pass reads slot 0 as h_{-1} = 0 / c_{-1} = 0
+            c_all[0].zero_()
         if fused:
             wp, bp = cache.get(("lstm", dt), (weight, bias), lambda: ops.pack_lstm_weight(weight, bias, dt))
             if ops.PERSISTENT_LSTM:
@@ -336,7 +339,7 @@ class ConvLSTMSeq(torch.autograd.Function):
                     first_zero = (t == 0 and not have_h0)
                     ops.lstm_cell_fwd_fused(x_seq[t], None if first_zero else h_all[t],
                                             None if first_zero else c_all[t], wp, bp, c_all[t + 1], h_all[t + 1],
-                                            gates[t], ks)
+                                            None if gates is None else gates[t], ks)
         else:
             wp = cache.get(("fwd", dt, Cin + Ch), (weight,), lambda: ops.pack_conv_weight(weight, dt))
             zbuf = torch.empty((B, H, W, 4 * Ch), device=dev, dtype=torch.float32)
@@ -366,6 +369,12 @@ class ConvLSTMSeq(torch.autograd.Function):
         dc_next = None if dc_T is None else _c(dc_T).float()
         wd = ctx.cache.get(("dgrad", dt, Cin + Ch), (weight,), lambda: ops.pack_conv_weight_dgrad(weight, dt))
         dz_all = torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
+        if gates is None:
+            # gate recompute: all T steps in one launch, into the buffer the gate-gradient kernel overwrites with dz
+            # (element for element in place: every thread reads its four gates before it writes its four dz)
+            wp, bp = ctx.cache.get(("lstm", dt), (weight, ctx.bias), lambda: ops.pack_lstm_weight(weight, ctx.bias, dt))
+            ops.lstm_gates_recompute(x_seq, h_all, c_all, wp, bp, dz_all, ks)
+            gates = dz_all
         need_dx = ctx.needs_input_grad[0]
         dx_seq = torch.empty_like(x_seq) if need_dx else None
         if ops.lstm_seq_bwd_ok(x_seq, Ch):

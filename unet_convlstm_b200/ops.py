@@ -40,7 +40,9 @@ def act_dtype() -> torch.dtype:
 # helpers
 # ------------------------------------------------------------------------------------------------
 def _p(t):
-    return None if t is None else t.data_ptr()
+    """A pointer argument of a C-ABI call: the tensor itself (unet_convlstm_b200._lib.call hands it to the torch custom op,
+    or takes its data_ptr() on the ctypes route)."""
+    return t
 
 
 def bump_version(*tensors):
@@ -655,6 +657,28 @@ def lstm_seq_fwd_fused(x_seq, h_all, c_all, wp_il, bias_il, gates, have_h0, ksiz
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         timer.append((e0, e1, fl))
+
+
+# Gate recompute (north_star "gate-gradient recompute"): do not keep the activated gates [T, P, 4*Ch] of every ConvLSTM
+# layer between forward and backward; BPTT recomputes them for all T steps in one tensor-core launch from the stored
+# x_t / h_{t-1} / c_{t-1} (the steps are independent once the states are known) into the buffer the gate-gradient
+# kernel then overwrites with dz.  Costs one extra forward gate conv per layer (+1/3 of the cell FLOPs), saves
+# T*P*4*Ch*2 bytes of activation memory per layer.  Off by default (speed); B200_GATE_RECOMPUTE=1 or set_gate_recompute().
+GATE_RECOMPUTE = os.environ.get("B200_GATE_RECOMPUTE", "0") == "1"
+
+
+def set_gate_recompute(on: bool) -> None:
+    global GATE_RECOMPUTE
+    GATE_RECOMPUTE = bool(on)
+
+
+def lstm_gates_recompute(x_seq, h_all, c_all, wp_il, bias_il, gates_out, ksize):
+    """Activated gates of all T steps of a layer from its stored states (BPTT with GATE_RECOMPUTE)."""
+    T, B, H, W, Cin = x_seq.shape
+    Ch = c_all.shape[-1]
+    fl = 2.0 * T * B * H * W * ksize * ksize * 4 * Ch * (Cin + Ch)
+    _lib.call("b200_convlstm_gates_recompute_tc", _p(x_seq), Cin, _p(h_all), Ch, T, B, H, W, _p(wp_il), _p(bias_il),
+              _p(c_all), _p(gates_out), ksize, _st(), tag=f"Ch{Ch} {H}x{W} T{T}", work=(fl, None))
 
 
 def lstm_seq_bwd_ok(x_seq, Ch) -> bool:
