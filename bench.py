@@ -240,15 +240,19 @@ def run_reference_arm(args, out):
 
 
 def workload_config(args, batch_per_step=None):
+    shape = (args.size, args.seq_len, args.batch, args.base_ch)
+    which = {(64, 20, 256, 64): "BASELINE.json configs[1]", (128, 10, 32, 64): "BASELINE.json configs[2] shape",
+             (256, 16, 8, 128): "BASELINE.json configs[3] shape"}.get(shape, "custom shape")
+    kind = "Moving-MNIST-shaped" if args.size == 64 else "cloud-sequence-shaped (synthetic blobs)"
     return {
-        "workload": f"Moving-MNIST-shaped UNet-ConvLSTM {args.size}x{args.size}, T={args.seq_len}, "
-                    f"batch {args.batch} per GPU, base_ch {args.base_ch} + skip ConvLSTMs (BASELINE.json configs[1])",
+        "workload": f"{kind} UNet-ConvLSTM {args.size}x{args.size}, T={args.seq_len}, "
+                    f"batch {args.batch} per GPU, base_ch {args.base_ch} + skip ConvLSTMs ({which})",
         "batch_per_gpu": args.batch if batch_per_step is None else batch_per_step, "seq_len": args.seq_len,
         "image": args.size, "base_ch": args.base_ch, "use_skip_lstm": True, "precision": args.precision,
         "step": "the reference's training step (main.py:94-108): forward, compute_loss (weighted L1 + gradient loss, "
                 "masked), backward, clip_grad_norm_(1.0) + AdamW (multi-tensor kernels) update; gradient all-reduce overlapped when N > 1",
         "parallelism": f"dp{args.gpus}",
-        "l2": "per-step working set (tens of GB of activations, 168 MB of inputs) far exceeds the 126 MB L2",
+        "l2": "per-step working set (tens of GB of activations, 168 MB of inputs at configs[1]) far exceeds the 126 MB L2",
     }
 
 

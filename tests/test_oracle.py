@@ -265,9 +265,9 @@ def test_optimizer_oracle_matches_torch_clip_and_adamw():
 
 
 def test_weight_cache_invalidation_rules():
-    """functional.WeightCache on CPU tensors (pure host logic): version bumps, the emptied cache at the first forward
-    after a backward (torch's fused optimizers do not bump versions), and the single-use bookkeeping that gates the
-    background weight-gradient stream."""
+    """functional.WeightCache on CPU tensors (pure host logic): version bumps, the optimizer-step generation counter
+    (torch's fused optimizers do not bump versions), and the single-use bookkeeping that gates the background
+    weight-gradient stream."""
     import torch
     from unet_convlstm_b200.functional import WeightCache
     w = torch.nn.Parameter(torch.zeros(4))
@@ -279,15 +279,25 @@ def test_weight_cache_invalidation_rules():
     c.begin_forward(True)
     assert get() == 1 and get() == 1                      # cached within a step
     assert c.note_backward() is True                      # one use of the weights in this graph
-    c.begin_forward(True)                                 # the next step starts from an empty cache
-    assert get() == 2
+    c.begin_forward(False)                                # backward -> no-grad forward -> optimizer.step() -> forward
+    assert get() == 1                                     # (nothing changed yet: still cached)
+    opt = torch.optim.AdamW([w], lr=0.1, fused=False)
+    w.grad = torch.ones(4)
+    opt.step()
+    c.begin_forward(True)
+    assert get() == 2                                     # any optimizer step invalidates, version bump or not
     assert c.note_backward() is True
-    c.begin_forward(False)                                # ... and so does an evaluation pass after training
-    assert get() == 3
     c.begin_forward(False)
-    assert get() == 3                                     # inference keeps its packed weights
+    assert get() == 2
+    c.begin_forward(False)
+    assert get() == 2                                     # inference after training keeps its packed weights
     with torch.no_grad():
         w.add_(1.0)                                       # an in-place torch op bumps the version
+    assert get() == 3
+    from unet_convlstm_b200 import functional as Fn
+    g0 = Fn._OPT_GENERATION[0]
+    torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1).step()   # somebody else's optimizer: conservative
+    assert Fn._OPT_GENERATION[0] == g0 + 1
     assert get() == 4
     c.begin_forward(True), c.begin_forward(True)          # the module called twice in one graph
     assert c.note_backward() is False and c.note_backward() is False

@@ -135,8 +135,14 @@ class DoubleConv(nn.Module):
                                                 bn.eps, conv.bias))
             return ops.conv_affine_relu(Fn._c(x0), None if x1 is None else Fn._c(x1), wp, scale, shift,
                                         conv.kernel_size[0])
+        # momentum=None is torch's cumulative moving average (factor 1 / num_batches_tracked): encoded for the finalize
+        # kernel as -(n0 + 1), n0 = the count before this call (one BatchNorm call per timestep, so step t uses n0 + t + 1)
+        if bn.momentum is not None:
+            momentum = float(bn.momentum)
+        else:
+            momentum = -(float(bn.num_batches_tracked) + 1.0) if bn.track_running_stats else 0.0
         y = Fn.ConvBnRelu.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                training, bn.eps, bn.momentum if bn.momentum is not None else 0.1, self._caches[i])
+                                training, bn.eps, momentum, self._caches[i])
         if training and bn.track_running_stats:
             bn.num_batches_tracked += T  # one BatchNorm call per timestep in the reference
         return y

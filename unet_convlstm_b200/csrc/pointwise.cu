@@ -433,7 +433,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
         shift[c] = bt - m * gm * rs;
         return;
     }
-    double rm = running_mean[c], rv = running_var[c];
+    // running statistics are optional (track_running_stats=False); momentum < 0 encodes nn.BatchNorm2d(momentum=None),
+    // the cumulative moving average: momentum = -(n0 + 1) with n0 = num_batches_tracked before this call, and the
+    // update factor of step t is 1 / (n0 + t + 1)
+    const bool track = running_mean != nullptr && running_var != nullptr;
+    double rm = track ? running_mean[c] : 0.0, rv = track ? running_var[c] : 0.0;
     for (int t = 0; t < T_; ++t) {
         const double m = sum[t * C + c] / n;
         double var = sumsq[t * C + c] / n - m * m;
@@ -446,11 +450,14 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
         shift[t * C + c] = static_cast<float>(bt - m * gm * rs);
         const double unb = n > 1 ? var * (static_cast<double>(n) / (n - 1)) : var;
         // fp32 rounding after each update, like the reference's fp32 buffers
-        rm = static_cast<float>((1.0 - momentum) * rm + momentum * m);
-        rv = static_cast<float>((1.0 - momentum) * rv + momentum * unb);
+        const double f = momentum >= 0.f ? static_cast<double>(momentum) : 1.0 / (static_cast<double>(-momentum) + t);
+        rm = static_cast<float>((1.0 - f) * rm + f * m);
+        rv = static_cast<float>((1.0 - f) * rv + f * unb);
     }
-    running_mean[c] = static_cast<float>(rm);
-    running_var[c] = static_cast<float>(rv);
+    if (track) {
+        running_mean[c] = static_cast<float>(rm);
+        running_var[c] = static_cast<float>(rv);
+    }
 }
 
 int launch_bn_finalize(const double* sum, const double* sumsq, int T_, long long n, int C, const float* gamma,

@@ -11,24 +11,35 @@ import torch
 from . import ops
 
 
+# Every torch.optim.Optimizer.step() -- including the FUSED implementations (`torch._fused_adamw_` ...), which update
+# parameters WITHOUT touching their version counters -- bumps this generation through a global post-step hook.
+_OPT_GENERATION = [0]
+
+
+def _bump_generation(*_a, **_k):
+    _OPT_GENERATION[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_step_hook  # noqa: E402
+
+_reg_step_hook(_bump_generation)
+
+
 class WeightCache:
     """Packed (GEMM-layout, activation-dtype) copies of a module's parameters, rebuilt when the parameter changes.
-    Two signals: the tensor version (in-place torch ops, load_state_dict, this package's optimizer), and -- because
-    torch's FUSED optimizers (`torch._fused_adamw_` ...) update parameters WITHOUT touching the version counter -- a
-    completed backward pass: the first differentiated forward after a backward through the module starts from an
-    empty cache (a parameter update can only follow a backward; re-packing is ~1 % of a training step)."""
+    Two signals: the tensor version (in-place torch ops, load_state_dict, this package's optimizer) and the optimizer
+    generation above (any torch optimizer step).  Round 1 instead emptied the cache at the first forward after a
+    backward; a no-grad forward between backward and optimizer.step() consumed that flag and the next training
+    forward used stale packed weights -- the generation counter has no such window, and an evaluation
+    loop after training keeps its packed weights."""
 
     def __init__(self):
         self._d = {}
         self._open = 0        # forward passes (with a graph) whose backward has not run yet
         self._shared = False  # the parameters were used more than once in the graph(s) still open
-        self._dirty = False   # a backward ran since the cache was filled: an optimizer may have stepped
 
     def begin_forward(self, differentiated: bool) -> bool:
         """Call at the top of every forward pass, BEFORE the first get().  Returns `differentiated`."""
-        if self._dirty:
-            self._d.clear()
-            self._dirty = False
         if differentiated:
             self._open += 1
             if self._open > 1:
@@ -40,14 +51,13 @@ class WeightCache:
         several contributions on the current stream, which rules out producing one of them on the background
         stream, ops.background)."""
         single = not self._shared
-        self._dirty = True
         self._open = max(0, self._open - 1)
         if self._open == 0:
             self._shared = False
         return single
 
     def get(self, key, params, builder):
-        ver = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        ver = (_OPT_GENERATION[0],) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
         hit = self._d.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]

@@ -334,7 +334,7 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
                   _p(running_var), eps, momentum, 1, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
         # the kernel wrote the running estimates through raw pointers: tell autograd's version counters, which
         # the folded-BatchNorm cache of the inference path (and anyone else) relies on
-        bump_version(running_mean, running_var)
+        bump_version(running_mean, running_var)   # (None when track_running_stats=False: nothing to update)
     else:
         _lib.call("b200_bn_finalize", None, None, 1, P, C, _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), eps, momentum, 0, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
