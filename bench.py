@@ -317,15 +317,42 @@ def run_b200_arm(args, out):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_profile = {}
+
+    def timed(fn, steps, tag=None):
+        """K steps between two barriers, timed on the device with CUDA events, max over ranks.  One extra event per step
+        gives the per-step durations of this rank (`tag`: kept in step_profile, gathered over the ranks for the JSON line)."""
+        import gc
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        st0 = torch.cuda.memory_stats(dev)
+        gc0 = [g["collections"] for g in gc.get_stats()]
+        host = [time.perf_counter()]
+        ev[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            ev[i + 1].record()
+            host.append(time.perf_counter())
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        st1 = torch.cuda.memory_stats(dev)
+        gc1 = [g["collections"] for g in gc.get_stats()]
+        ms = torch.tensor([ev[0].elapsed_time(ev[-1])], device=dev)
+        if tag is not None:
+            step_profile[tag + "_host"] = {
+                "cudaMalloc_calls": st1.get("num_device_alloc", 0) - st0.get("num_device_alloc", 0),
+                "cudaFree_calls": st1.get("num_device_free", 0) - st0.get("num_device_free", 0),
+                "alloc_retries": st1.get("num_alloc_retries", 0) - st0.get("num_alloc_retries", 0),
+                "gc_collections": [b - a for a, b in zip(gc0, gc1)],
+                "rank0_host_ms_per_step": [round((host[i + 1] - host[i]) * 1e3, 1) for i in range(steps)]}
+            per = torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)], device=dev)
+            if world > 1:
+                allp = [torch.empty_like(per) for _ in range(world)]
+                dist.all_gather(allp, per)
+            else:
+                allp = [per]
+            step_profile[tag] = {"per_rank_median_ms": [round(float(q.median()), 2) for q in allp],
+                                 "per_rank_max_ms": [round(float(q.max()), 2) for q in allp],
+                                 "rank0_steps_ms": [round(float(v), 1) for v in per.tolist()]}
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
@@ -383,7 +410,7 @@ def run_b200_arm(args, out):
     # ---- eager region: every launch from Python, CUDA events around each fused cell launch (roofline) ----
     ops.CELL_TIMER = []
     calls0 = _lib.kernel_launches()
-    ms_eager = timed(lambda: step(x_dev, y_dev, m_dev), args.steps)
+    ms_eager = timed(lambda: step(x_dev, y_dev, m_dev), args.steps, tag="value")
     launches = _lib.kernel_launches() - calls0
     cell_events, ops.CELL_TIMER = ops.CELL_TIMER, None
     torch.cuda.synchronize()
@@ -391,7 +418,7 @@ def run_b200_arm(args, out):
     cell_flops = [fl for _, _, fl in cell_events]
 
     # ---- fwd+bwd only (no optimizer), for the record --------------------------------------------
-    ms_fb = timed(lambda: step(x_dev, y_dev, m_dev, with_opt=False), max(1, args.steps // 2))
+    ms_fb = timed(lambda: step(x_dev, y_dev, m_dev, with_opt=False), max(1, args.steps // 2), tag="fwd_bwd_only")
     # ---- timed region 1: inputs resident in HBM = the eager region above.  (Round 1 could also replay the step from
     #      a CUDA graph; measured 232.7 ms graphed vs 233.3 ms eager -- the step is GPU-bound, the host runs ahead --
     #      so the graph path was removed in round 2.) ----
@@ -458,6 +485,7 @@ def run_b200_arm(args, out):
                          "flops_per_launch": max(cell_flops) if cell_flops else None,
                          "share_of_step": (sum(cell_ms) / args.steps / ms_eager) if cell_ms else None},
             "clocks": clocks,
+            "step_profile": step_profile,
             "peak_mem_gb": peak_mem / 2 ** 30,
         }
         if world == 1 and not args.no_cpu_baseline:

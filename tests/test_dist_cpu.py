@@ -77,3 +77,21 @@ def test_grad_reducer_single_process_is_identity():
     ((m2(x) - y) ** 2).mean().backward()
     for a, b in zip(m.parameters(), m2.parameters()):
         assert torch.equal(a.grad, b.grad)
+
+
+def test_make_loaders_shard_the_dataset_per_rank():
+    """loop.make_loaders: every rank builds the same split; the per-rank samplers partition the training part
+    (per-rank DistributedSampler)."""
+    from torch.utils.data import TensorDataset
+    from unet_convlstm_b200.loop import make_loaders
+    ds = TensorDataset(torch.arange(40).float().view(40, 1))
+    seen = []
+    for rank in range(4):
+        tr, va = make_loaders(ds, batch_size=3, rank=rank, world=4)
+        tr.sampler.set_epoch(0)
+        seen.append(sorted(int(v) for (b,) in tr for v in b.view(-1)))
+        assert sum(len(b[0]) for b in va) == 2                      # 8 validation items over 4 ranks
+    flat = sorted(v for s in seen for v in s)
+    assert len(flat) == 32 and len(set(flat)) == 32                 # 80 % of 40, each item on exactly one rank
+    tr1, va1 = make_loaders(ds, batch_size=3, rank=0, world=1)
+    assert sorted(int(v) for (b,) in tr1 for v in b.view(-1)) == flat   # same split as the single-process loaders

@@ -99,6 +99,30 @@ def _device_batches(loader, device):
         cur, staged = nxt_dev, nxt_staged
 
 
+def make_loaders(dataset, batch_size, seed=42, train_fraction=0.8, rank=None, world=None):
+    """The data pipeline of main.py:241-246 for one rank of a data-parallel job: the same 80/20 random split on every
+    rank (seeded -- main.py splits unseeded, a single process does not care), then a per-rank DistributedSampler over
+    the training part (shuffled, re-seeded per epoch by `loader.sampler.set_epoch(e)`) and over the validation part
+    (in order).  `batch_size` is per rank.  With world == 1 this is exactly main.py's pair of DataLoaders."""
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader, DistributedSampler, random_split
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if world > 1 else 0
+    n_train = int(train_fraction * len(dataset))
+    gen = torch.Generator().manual_seed(seed)
+    train_ds, val_ds = random_split(dataset, [n_train, len(dataset) - n_train], generator=gen)
+    if world == 1:
+        g2 = torch.Generator().manual_seed(seed)
+        return (DataLoader(train_ds, batch_size=batch_size, shuffle=True, pin_memory=True, generator=g2),
+                DataLoader(val_ds, batch_size=batch_size, shuffle=False, pin_memory=True))
+    ts = DistributedSampler(train_ds, num_replicas=world, rank=rank, shuffle=True, seed=seed, drop_last=False)
+    vs = DistributedSampler(val_ds, num_replicas=world, rank=rank, shuffle=False, drop_last=False)
+    return (DataLoader(train_ds, batch_size=batch_size, sampler=ts, pin_memory=True),
+            DataLoader(val_ds, batch_size=batch_size, sampler=vs, pin_memory=True))
+
+
 def _stack(output):
     return torch.stack(output, dim=1) if isinstance(output, (list, tuple)) else output
 

@@ -602,9 +602,36 @@ class background:
 _bg_delivered: list = []
 
 
+# Host lead limit.  Tensors that cross to the background stream (ops.background inputs / outputs: record_stream) return to
+# the caching allocator's pool only once the GPU has passed their last use.  A GPU-bound training loop that never
+# synchronises (no loss.item()) lets the host run ~2 steps ahead of the GPU: it frees and re-allocates those blocks long
+# before they are reusable, the allocator answers with fresh cudaMalloc calls, the reserved pool creeps up to the whole
+# HBM and then stalls for 0.1-0.8 s in its out-of-memory retry (free everything, synchronise, malloc again) -- measured
+# on B200 in bench.py's non-synchronising regions: 37-199 cudaMalloc calls and 3 retries inside the timed steps, single
+# steps of 289-794 ms among 207 ms ones, the whole 8-GPU job waiting for whichever rank stalled
+# (profiles/r02_allocator_stalls.md).  So the end of every backward pass that used the background stream waits, on the
+# HOST, for the end of the PREVIOUS such backward: the host stays at most one step ahead (the GPU still has a full step
+# queued), and the cross-stream working set is bounded by two steps.
+_lead_events: dict = {}
+HOST_LEAD_LIMIT = os.environ.get("B200_HOST_LEAD_LIMIT", "1") != "0"
+
+
+def _limit_host_lead():
+    if not HOST_LEAD_LIMIT:
+        return
+    dev = torch.cuda.current_device()
+    prev = _lead_events.get(dev)
+    if prev is not None:
+        prev.synchronize()
+    ev = torch.cuda.Event()
+    ev.record()
+    _lead_events[dev] = ev
+
+
 def _end_of_backward_join():
     _bg_joined_task[0] = -1
     background_join()
+    _limit_host_lead()
     # AccumulateGrad must have STORED each background gradient (same storage).  Had it cloned or accumulated instead
     # (a second reference to the gradient, mismatching strides, a .grad that appeared meanwhile), that kernel ran on
     # the current stream while the background stream was still writing: corrupt, so fail loudly.
