@@ -520,7 +520,7 @@ def main():
     ap.add_argument("--seq-len", type=int, default=20)
     ap.add_argument("--size", type=int, default=64)
     ap.add_argument("--base-ch", type=int, default=64)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="sequences in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")

@@ -90,6 +90,24 @@ int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all, int Ch, in
                              const void* wpacked, const float* bias_packed, float* c_all, void* gates,
                              int have_h0, int ksize, void* stream);
 
+/* ---- "tf32" precision mode (north_star: "bf16/TF32 inputs with fp32 accumulation"; the reference's own GPU numerics:
+ * torch enables TF32 in cuDNN convolutions by default).  Same implicit GEMM as the *_tc entry points with fp32 tensors
+ * everywhere: sources, packed weights ([k*k][N][C0+C1], gate-interleaved for the cell), outputs, h and the activated
+ * gates; the products are tcgen05 kind::tf32 (10-bit mantissa), the accumulation fp32.  Channel counts must be
+ * multiples of 8 (K blocks of 32 / 16 / 8 channels = rows of 128 / 64 / 32 bytes). ---- */
+int b200_conv_tf32_supported(int B, int H, int W, int C0, int C1, int N, int lstm);
+int b200_conv_tf32_fwd(const float* src0, int C0, const float* src1, int C1, int T, int B, int H, int W,
+                       const float* wpacked, const float* bias, int N, int ksize, float* dst0, long long ld0, int split,
+                       float* dst1, long long ld1, int relu, int accumulate, void* stream);
+/* Weight gradient in the tf32 mode; arguments as b200_wgrad_tc with fp32 dz / src (dw zero-initialised by the caller). */
+int b200_wgrad_tf32_supported(int B, int H, int W, int Nz, int Csrc);
+int b200_wgrad_tf32(const float* dz, int Nz, const float* src, int Csrc, int T, int B, int H, int W, int ksize, float* dw,
+                    long long ldk, int koff, void* stream);
+/* One fused ConvLSTM cell step (unet.py:21-36) in the tf32 mode; arguments as b200_convlstm_cell_fwd_tc. */
+int b200_convlstm_cell_fwd_tf32(const float* x, int Cin, const float* h_prev, int Ch, int B, int H, int W,
+                                const float* wpacked, const float* bias_packed, const float* c_prev, float* c_next,
+                                float* h_next, float* gates_out, int ksize, void* stream);
+
 /* Gate recompute for BPTT (north_star "gate-gradient recompute"; the reference's autograd instead keeps the four
  * activated gates of every step, unet.py:29-33): the activated gates of ALL T steps from the stored x_t, h_{t-1}
  * (h_all slot t) and c_{t-1} (c_all slot t) in one tensor-core launch -- the steps are independent once the states

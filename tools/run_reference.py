@@ -313,7 +313,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("script", choices=["overfit", "main", "get_metrics"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--batch-size", type=int, default=8)

@@ -42,7 +42,11 @@ def _to_nchw(y: torch.Tensor) -> torch.Tensor:
 
 def _in_pad(c: int) -> int | None:
     """bf16 mode: the first conv's few input channels are zero-padded to one tensor-core K chunk."""
-    return 16 if (ops.get_precision() == "bf16" and c < 16) else None
+    if ops.get_precision() == "bf16":
+        return 16 if c < 16 else None
+    if ops.get_precision() == "tf32":
+        return 8 if c < 8 else None      # one tf32 K block (32 bytes)
+    return None
 
 
 # -----------------------------------------------------------------------------------------------

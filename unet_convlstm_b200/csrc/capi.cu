@@ -11,7 +11,7 @@ using namespace b200;
 
 namespace b200 {
 int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
-                    int ksize, float* dw, long long ldk, int koff, cudaStream_t stream);
+                    int ksize, float* dw, long long ldk, int koff, cudaStream_t stream, int in_fp32 = 0);
 // wgrad_halo.cu: 64-channel 3x3 layers, source tile loaded once per pixel block
 bool wgrad_halo_supported(int Nz, int Csrc, int B, int H, int W, int ksize);
 int launch_wgrad_halo(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W, float* dw,
@@ -211,6 +211,59 @@ extern "C" int b200_convlstm_seq_fwd_tc(const void* x_seq, int Cin, void* h_all,
     return launch_convlstm_seq_tc(x_seq, h_all, wpacked, p, static_cast<cudaStream_t>(stream));
 }
 
+// ------------------------------------------------------------------------------------------------
+// "tf32" precision mode: fp32 tensors, tcgen05 kind::tf32 products, fp32 accumulation
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_conv_tf32_supported(int B, int H, int W, int C0, int C1, int N, int lstm) {
+    MTile mt;
+    if (!plan_mtile(B, H, W, 128, &mt)) return 0;
+    if (C0 <= 0 || C0 % 8 != 0 || C1 % 8 != 0) return 0;
+    if (pick_block_n(N, lstm ? EPI_LSTM : EPI_STORE) == 0) return 0;
+    return 1;
+}
+
+extern "C" int b200_conv_tf32_fwd(const float* src0, int C0, const float* src1, int C1, int T, int B, int H, int W,
+                                  const float* wpacked, const float* bias, int N, int ksize, float* dst0, long long ld0,
+                                  int split, float* dst1, long long ld1, int relu, int accumulate, void* stream) {
+    if (!src0 || !wpacked || !dst0 || T <= 0 || N <= 0 || (ksize & 1) == 0) {
+        set_last_error("b200_conv_tf32_fwd: bad arguments");
+        return B200_ERR_ARG;
+    }
+    if (split < 0 || split > N || (split < N && !dst1) || split % 16 != 0 || ld0 % 4 != 0 || (split < N && ld1 % 4 != 0)) {
+        set_last_error("b200_conv_tf32_fwd: bad split/ld (split=%d N=%d ld0=%lld ld1=%lld)", split, N, ld0, ld1);
+        return B200_ERR_ARG;
+    }
+    ConvTcParams p = {};
+    p.T = T; p.B = B; p.H = H; p.W = W;
+    p.C0 = C0; p.C1 = C1; p.N = N; p.ksize = ksize;
+    p.dst0 = dst0; p.dst1 = dst1; p.ld0 = ld0; p.ld1 = ld1;
+    p.split = split;
+    p.out_fp32 = 1; p.relu = relu; p.accumulate = accumulate;
+    p.bias = bias;
+    p.in_fp32 = 1;
+    return launch_conv_tc(src0, src1, wpacked, p, EPI_STORE, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_convlstm_cell_fwd_tf32(const float* x, int Cin, const float* h_prev, int Ch, int B, int H, int W,
+                                           const float* wpacked, const float* bias_packed, const float* c_prev,
+                                           float* c_next, float* h_next, float* gates_out, int ksize, void* stream) {
+    if (!x || !wpacked || !c_next || !h_next || Ch <= 0 || Cin <= 0) {
+        set_last_error("b200_convlstm_cell_fwd_tf32: bad arguments");
+        return B200_ERR_ARG;
+    }
+    ConvTcParams p = {};
+    p.T = 1; p.B = B; p.H = H; p.W = W;
+    p.C0 = Cin; p.C1 = h_prev ? Ch : 0;
+    p.N = 4 * Ch; p.ksize = ksize;
+    p.wK = Cin + Ch;
+    p.bias = bias_packed;
+    p.c_prev = c_prev; p.c_next = c_next;
+    p.h_next = reinterpret_cast<__nv_bfloat16*>(h_next);       // fp32 tensors: see ConvTcParams::state_fp32
+    p.gates_out = reinterpret_cast<__nv_bfloat16*>(gates_out);
+    p.in_fp32 = 1; p.state_fp32 = 1;
+    return launch_conv_tc(x, h_prev, wpacked, p, EPI_LSTM, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_convlstm_gates_recompute_tc(const void* x_seq, int Cin, const void* h_all, int Ch, int T, int B, int H,
                                                 int W, const void* wpacked, const float* bias_packed, const float* c_all,
                                                 void* gates_out, int ksize, void* stream) {
@@ -284,6 +337,24 @@ extern "C" int b200_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, 
         return launch_wgrad_tc2(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff, static_cast<cudaStream_t>(stream));
     return launch_wgrad_tc(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff,
                            static_cast<cudaStream_t>(stream));
+}
+
+// "tf32" precision mode: the weight gradient from fp32 dz / src on tcgen05 kind::tf32 (MN-major operands, 32 pixels per
+// pipeline stage); 1-CTA kernel only
+extern "C" int b200_wgrad_tf32_supported(int B, int H, int W, int Nz, int Csrc) {
+    MTile mt;
+    if (!plan_mtile(B, H, W, 32, &mt)) return 0;
+    if (Nz <= 0 || Csrc <= 0 || Nz % 32 != 0 || Csrc % 32 != 0) return 0;   // 128-byte pixel rows (see wgrad_tc.cu)
+    return 1;
+}
+
+extern "C" int b200_wgrad_tf32(const float* dz, int Nz, const float* src, int Csrc, int T, int B, int H, int W, int ksize,
+                               float* dw, long long ldk, int koff, void* stream) {
+    if (!dz || !src || !dw || Nz <= 0 || Csrc <= 0 || (ksize & 1) == 0 || koff < 0 || koff + Csrc > ldk) {
+        set_last_error("b200_wgrad_tf32: bad arguments");
+        return B200_ERR_ARG;
+    }
+    return launch_wgrad_tc(dz, Nz, src, Csrc, T, B, H, W, ksize, dw, ldk, koff, static_cast<cudaStream_t>(stream), 1);
 }
 
 extern "C" int b200_wgrad_tc_supported(int B, int H, int W, int Nz, int Csrc) {

@@ -193,7 +193,7 @@ void tmap_cache_stats(unsigned long long* hits, unsigned long long* misses) {
 }
 
 int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
-                 const uint64_t strides_elems[4], const uint32_t box[5]) {
+                 const uint64_t strides_elems[4], const uint32_t box[5], int esize, int atom32) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_last_error("cuTensorMapEncodeTiled entry point not available");
@@ -206,7 +206,7 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
     TmapKey key;
     memset(&key, 0, sizeof(key));
     key.base = base;
-    key.rank = 5;
+    key.rank = 5u | (uint32_t(esize) << 8) | (uint32_t(atom32) << 16);
     for (int i = 0; i < 5; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
     for (int i = 0; i < 4; ++i) key.s[i] = strides_elems[i];
     if (tmap_lookup(key, out)) return B200_OK;
@@ -218,15 +218,19 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
         estr[i] = 1;
     }
     for (int i = 0; i < 4; ++i) {
-        gstr[i] = strides_elems[i] * 2;  // bf16
+        gstr[i] = strides_elems[i] * uint64_t(esize);  // bf16 (2) or fp32 (4)
         if (gstr[i] % 16 != 0) {
             set_last_error("TMA stride %d = %llu bytes not a multiple of 16", i,
                            (unsigned long long)gstr[i]);
             return B200_ERR_ALIGN;
         }
     }
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bx,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(int(box[0]) * 2),
+    CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                    const_cast<void*>(base), gdim, gstr, bx,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    // atom32: the 128-byte swizzle on 32-byte atoms (4-row period) -- what an MN-major operand of 32-bit
+                    // elements needs (UMMA layout type SWIZZLE_128B_BASE32B, wgrad_tc.cu tf32 mode)
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_for_bytes(int(box[0]) * esize),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error(
@@ -241,37 +245,38 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
 }
 
 int make_act_tmap(CUtensorMap* out, const void* base, int C, int W, int H, int B, int T, int box_c,
-                  int Wt, int Ht, int Bt) {
+                  int Wt, int Ht, int Bt, int esize, int atom32) {
     uint64_t dims[5] = {uint64_t(C), uint64_t(W), uint64_t(H), uint64_t(B), uint64_t(T)};
     uint64_t str[4] = {uint64_t(C), uint64_t(C) * W, uint64_t(C) * W * H, uint64_t(C) * W * H * B};
     uint32_t box[5] = {uint32_t(box_c), uint32_t(Wt), uint32_t(Ht), uint32_t(Bt), 1u};
-    return make_tmap_5d(out, base, dims, str, box);
+    return make_tmap_5d(out, base, dims, str, box, esize, atom32);
 }
 
 int make_w_tmap(CUtensorMap* out, const void* base, int K, int rows, int taps, int box_k,
-                int box_rows) {
+                int box_rows, int esize) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_last_error("cuTensorMapEncodeTiled entry point not available");
         return B200_ERR_CUDA;
     }
-    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (K % 8) != 0) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((K * esize) % 16) != 0) {
         set_last_error("weight TMA map: base %p / K=%d misaligned", base, K);
         return B200_ERR_ALIGN;
     }
     TmapKey key;
     memset(&key, 0, sizeof(key));
     key.base = base;
-    key.rank = 3;
+    key.rank = 3u | (uint32_t(esize) << 8);
     key.d[0] = uint64_t(K); key.d[1] = uint64_t(rows); key.d[2] = uint64_t(taps);
     key.b[0] = uint32_t(box_k); key.b[1] = uint32_t(box_rows); key.b[2] = 1;
     if (tmap_lookup(key, out)) return B200_OK;
     cuuint64_t gdim[3] = {cuuint64_t(K), cuuint64_t(rows), cuuint64_t(taps)};
-    cuuint64_t gstr[2] = {cuuint64_t(K) * 2, cuuint64_t(K) * 2 * rows};
+    cuuint64_t gstr[2] = {cuuint64_t(K) * esize, cuuint64_t(K) * esize * rows};
     cuuint32_t bx[3] = {cuuint32_t(box_k), cuuint32_t(box_rows), 1u};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, bx,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_k * 2),
+    CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                    const_cast<void*>(base), gdim, gstr, bx,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_k * esize),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(3d weights) failed: %d K=%d rows=%d taps=%d box={%d,%d}",

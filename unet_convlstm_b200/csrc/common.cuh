@@ -48,13 +48,13 @@ unsigned* device_sync_counter(cudaStream_t stream);  // step counter of the time
 // ---- TMA tensor-map construction (driver entry point resolved at run time, no libcuda link) ----
 // Activation map over a bf16 NHWC tensor viewed as {C, W, H, B, T}; box = {box_c, Wt, Ht, Bt, 1}.
 int make_act_tmap(CUtensorMap* out, const void* base, int C, int W, int H, int B, int T, int box_c,
-                  int Wt, int Ht, int Bt);
+                  int Wt, int Ht, int Bt, int esize = 2, int atom32 = 0);
 // General 5-D bf16 map with explicit element strides between dimensions (dims[0] is contiguous).
 int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
-                 const uint64_t strides_elems[4], const uint32_t box[5]);
+                 const uint64_t strides_elems[4], const uint32_t box[5], int esize = 2, int atom32 = 0);
 // Weight map over bf16 [taps][rows][K] viewed as {K, rows, taps}; box = {box_k, box_rows, 1}.
 int make_w_tmap(CUtensorMap* out, const void* base, int K, int rows, int taps, int box_k,
-                int box_rows);
+                int box_rows, int esize = 2);
 
 // hits / misses of the tensor-map cache since the library was loaded
 void tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);

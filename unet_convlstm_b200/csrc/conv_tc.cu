@@ -153,8 +153,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         if (n0 >= p.bwd_Cin) return t > 0 || p.bwd_dh0 != nullptr;
         return true;
     };
-    const uint32_t a_bytes = BLOCK_M * p.kc * 2;
-    const uint32_t b_bytes = BLOCK_N * p.kc * 2;
+    const uint32_t esize = p.in_fp32 ? 4u : 2u;  // operand element size: bf16 (kind::f16) or fp32 read as TF32 (kind::tf32)
+    const uint32_t a_bytes = BLOCK_M * p.kc * esize;
+    const uint32_t b_bytes = BLOCK_N * p.kc * esize;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_a0);
@@ -240,12 +241,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
         // converged warp, one elected lane issues (see the producer): back-to-back UTCHMMA
-        const uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-        // K-major swizzled operand tiles: rows of kc*2 bytes, 8-row atoms => SBO = 8 * row bytes
-        const uint32_t row_bytes = p.kc * 2;
-        const uint32_t layout_type = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
+        const bool tf32 = p.in_fp32 != 0;
+        const uint32_t idesc = tf32 ? make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0) : make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        // K-major swizzled operand tiles: rows of kc*esize bytes (128 / 64 / 32), 8-row atoms => SBO = 8 * row bytes
+        const uint32_t row_bytes = p.kc * esize;
+        const uint32_t layout_type = (row_bytes == 128) ? 2u : (row_bytes == 64 ? 4u : 6u);
         const uint32_t sbo = 8u * row_bytes;
-        const int mma_per_kb = p.kc / 16;
+        const int mma_per_kb = row_bytes / 32;  // one MMA = 32 bytes of K: 16 bf16 or 8 tf32
         // descriptor = constant high part | (smem address >> 4); only the address changes per stage
         const uint64_t desc_hi = make_smem_desc(0, 16, sbo, layout_type);
         int stage = 0;
@@ -274,7 +276,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     if (elect_one()) {
                         const uint64_t adesc = desc_hi | a_lo;
                         const uint64_t bdesc = desc_hi | (a_lo + B_LO);
-                        if (mma_per_kb == 4) {
+                        if (tf32) {
+                            for (int k = 0; k < mma_per_kb; ++k)
+                                umma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                                          k == 0 ? accum : 1u);
+                        } else if (mma_per_kb == 4) {
                             // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in >>4 units
                             umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
                             umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -622,6 +628,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                             for (int j = 0; j < 4; ++j)
                                 co[j] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
                         }
+                        if (p.state_fp32) {
+                            // "tf32" precision mode: h and the activated gates are fp32 tensors
+                            auto st16f = [](float* dst, const float* sv) {
+                                float4* o = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) o[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+                            };
+                            if (p.h_next) st16f(reinterpret_cast<float*>(p.h_next) + coff, hn);
+                            if (p.gates_out) {
+                                float* gb = reinterpret_cast<float*>(p.gates_out) + pix * (4LL * Ch) + ch;
+                                st16f(gb, gi);
+                                st16f(gb + Ch, gf);
+                                st16f(gb + 2 * Ch, gg);
+                                st16f(gb + 3 * Ch, go);
+                            }
+                            continue;
+                        }
                         if (p.h_next) {
                             uint4* ho = reinterpret_cast<uint4*>(p.h_next + coff);
                             ho[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
@@ -753,11 +776,17 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
         return B200_ERR_ARG;
     }
     const int Ct = p.wK > 0 ? p.wK : p.C0 + p.C1;
-    int kc = 64;
-    while (kc >= 16 && ((p.C0 % kc) != 0 || (p.C1 % kc) != 0)) kc >>= 1;
-    if (kc < 16 || p.C0 <= 0) {
-        set_last_error("conv_tc: channel counts C0=%d C1=%d are not multiples of 16", p.C0, p.C1);
+    const int esize = p.in_fp32 ? 4 : 2;
+    const int kc_max = 128 / esize, kc_min = 32 / esize;   // K-block rows of 128 .. 32 bytes
+    int kc = kc_max;
+    while (kc >= kc_min && ((p.C0 % kc) != 0 || (p.C1 % kc) != 0)) kc >>= 1;
+    if (kc < kc_min || p.C0 <= 0) {
+        set_last_error("conv_tc: channel counts C0=%d C1=%d are not multiples of %d", p.C0, p.C1, kc_min);
         return B200_ERR_SHAPE;
+    }
+    if (p.in_fp32 && (epi == EPI_LSTM_BWD || p.seq_T > 0 || p.stat_sum || p.shuf_C > 0 || !(p.out_fp32 || epi == EPI_LSTM))) {
+        set_last_error("conv_tc: the tf32 mode covers plain fp32-output convolutions and the single-step fused cell");
+        return B200_ERR_ARG;
     }
     p.kc = kc;
     const int block_n = pick_block_n(p.N, epi);
@@ -790,16 +819,16 @@ int launch_conv_tc(const void* src0, const void* src1, const void* wpacked, Conv
     p.err_flag = device_error_flag();
 
     CUtensorMap ta0, ta1, tb;
-    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt);
+    int rc = make_act_tmap(&ta0, src0, p.C0, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt, esize);
     if (rc != B200_OK) return rc;
     if (p.C1 > 0) {
-        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt);
+        rc = make_act_tmap(&ta1, src1, p.C1, p.W, p.H, p.B, map_T, kc, mt.Wt, mt.Ht, mt.Bt, esize);
         if (rc != B200_OK) return rc;
     } else {
         ta1 = ta0;
     }
     // rows beyond N inside the last N tile are TMA out-of-bounds reads => zero filled
-    rc = make_w_tmap(&tb, wpacked, Ct, p.N, p.ksize * p.ksize, kc, block_n);
+    rc = make_w_tmap(&tb, wpacked, Ct, p.N, p.ksize * p.ksize, kc, block_n, esize);
     if (rc != B200_OK) return rc;
 
     if (epi == EPI_LSTM) {

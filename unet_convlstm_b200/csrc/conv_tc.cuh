@@ -17,7 +17,10 @@ struct ConvTcParams {
     int C0, C1;       // channels of source 0 / source 1 (C1 == 0: single source)
     int N;            // GEMM N (output channels; 4*Ch for the LSTM epilogue)
     int ksize, pad;   // square filter size (odd) and padding
-    int kc;           // channels per K block (64 / 32 / 16)
+    int kc;           // channels per K block (bf16: 64 / 32 / 16; fp32 operands: 32 / 16 / 8 -- rows of 128 / 64 / 32 bytes)
+    int in_fp32;      // 1: sources and packed weights are fp32 and the MMA is tcgen05 kind::tf32 (the "tf32" precision
+                      // mode: fp32 storage, TF32 tensor-core products, fp32 accumulation); 0: bf16, kind::f16
+    int state_fp32;   // EPI_LSTM with in_fp32: h_next / gates_out are fp32 tensors
     int wK;           // row length of the packed weights (0: C0 + C1)
     // M tiling
     int Wt, Ht, Bt;

@@ -55,6 +55,8 @@ struct WgradParams {
     long long ldk;
     int koff;
     int* err_flag;
+    int in_fp32;     // 1: dz and src are fp32 tensors, tcgen05 kind::tf32 (the "tf32" precision mode); a pipeline stage
+                     // then holds 32 pixels instead of 64 -- the same bytes, the same four MMAs (K = 8 pixels each)
 };
 
 template <int BLOCK_N, bool STACKED>
@@ -134,8 +136,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     // A operand (M = 128): stacked -> source boxes, normal -> dz boxes
     const int cwA = STACKED ? p.cwV : p.cwS;
     const int cwB = STACKED ? p.cwS : p.cwV;
-    const uint32_t boxA_bytes = WG_RB * cwA * 2;
-    const uint32_t boxB_bytes = WG_RB * cwB * 2;
+    // bytes of one box = (pixels per stage) x (channel chunk) x (element size): 64 x cw x 2 (bf16) = 32 x cw x 4 (fp32)
+    const uint32_t esize = p.in_fp32 ? 4u : 2u;
+    const uint32_t boxA_bytes = 128u * cwA;
+    const uint32_t boxB_bytes = 128u * cwB;
     const uint32_t boxS_bytes = STACKED ? boxB_bytes : boxA_bytes;
     const uint32_t boxV_bytes = STACKED ? boxA_bytes : boxB_bytes;
     const int cwS = p.cwS, cwV = p.cwV;
@@ -294,13 +298,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     } else if (warp == 1) {
         // =================================== MMA issuer =====================================
         // converged warp, one elected lane issues (see the producer): back-to-back UTCHMMA
-        const uint32_t ltA = (cwA == 64) ? 2u : (cwA == 32 ? 4u : 6u);
-        const uint32_t ltB = (cwB == 64) ? 2u : (cwB == 32 ? 4u : 6u);
-        // descriptor = constant high part | (smem address >> 4); 16 pixels (one MMA K step) further
-        // down the box = two 8-row atoms = 16 * cw * 2 bytes
-        const uint64_t hiA = make_smem_desc(0, boxA_bytes, 8u * cwA * 2, ltA);
-        const uint64_t hiB = make_smem_desc(0, boxB_bytes, 8u * cwB * 2, ltB);
-        const uint32_t stepA = (16u * cwA * 2) >> 4, stepB = (16u * cwB * 2) >> 4;
+        // swizzle span = bytes of one pixel row of a box (cw channels): 128 / 64 / 32
+        const uint32_t rowA = cwA * esize, rowB = cwB * esize;
+        const uint32_t ltA = (rowA == 128) ? 2u : (rowA == 64 ? 4u : 6u);
+        const uint32_t ltB = (rowB == 128) ? 2u : (rowB == 64 ? 4u : 6u);
+        // descriptor = constant high part | (smem address >> 4); one MMA K step = 32 bytes of pixels per channel row
+        // = 16 bf16 pixels (two 8-row atoms) or 8 fp32 pixels (one atom) further down the box: 32 * cw bytes either way
+        // tf32: MN-major operands of 32-bit elements use the 128-byte swizzle on 32-byte atoms (UMMA layout type 1,
+        // SWIZZLE_128B_BASE32B; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 128-byte pixel rows (32 channels), swizzle
+        // period and stride-byte-offset = 4 pixel rows
+        const bool tf32 = p.in_fp32 != 0;
+        const uint64_t hiA = tf32 ? make_smem_desc(0, boxA_bytes, 4u * rowA, 1u) : make_smem_desc(0, boxA_bytes, 8u * rowA, ltA);
+        const uint64_t hiB = tf32 ? make_smem_desc(0, boxB_bytes, 4u * rowB, 1u) : make_smem_desc(0, boxB_bytes, 8u * rowB, ltB);
+        const uint32_t stepA = (32u * cwA) >> 4, stepB = (32u * cwB) >> 4;
         const uint32_t v_lo0 = (v_base & 0x3FFFFu) >> 4, s_lo0 = (s_base & 0x3FFFFu) >> 4;
         int sv = 0, ss = 0;
         uint32_t pv = 0, ps = 0, pt = 0;
@@ -308,7 +318,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             const WgUnit u = wg_decode<BLOCK_N, STACKED>(p, unit);
             const int ncols = STACKED ? u.scols : u.vcols;
             const int nmma = ((ncols + cwB - 1) / cwB) * cwB;  // whole loaded boxes
-            const uint32_t idesc = make_idesc_bf16(WG_BLOCK_M, nmma, 1, 1);
+            const uint32_t idesc = tf32 ? make_idesc_tf32(WG_BLOCK_M, nmma, 1, 1) : make_idesc_bf16(WG_BLOCK_M, nmma, 1, 1);
             const int rb_begin = u.split * p.rb_per_split;
             const int rb_end = min(rb_begin + p.rb_per_split, p.num_rblocks);
             mbar_wait(tempty, pt ^ 1u, p.err_flag, 4000 + 700);
@@ -325,10 +335,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                         const uint32_t v_lo = v_lo0 + sv * (Cfg::V_BYTES >> 4);
                         const uint64_t adesc = hiA | (STACKED ? v_lo : s_lo);
                         const uint64_t bdesc = hiB | (STACKED ? s_lo : v_lo);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                        umma_bf16(d_tmem, adesc + stepA, bdesc + stepB, idesc, 1u);
-                        umma_bf16(d_tmem, adesc + 2 * stepA, bdesc + 2 * stepB, idesc, 1u);
-                        umma_bf16(d_tmem, adesc + 3 * stepA, bdesc + 3 * stepB, idesc, 1u);
+                        if (tf32) {
+                            umma_tf32(d_tmem, adesc, bdesc, idesc, accum);
+                            umma_tf32(d_tmem, adesc + stepA, bdesc + stepB, idesc, 1u);
+                            umma_tf32(d_tmem, adesc + 2 * stepA, bdesc + 2 * stepB, idesc, 1u);
+                            umma_tf32(d_tmem, adesc + 3 * stepA, bdesc + 3 * stepB, idesc, 1u);
+                        } else {
+                            umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                            umma_bf16(d_tmem, adesc + stepA, bdesc + stepB, idesc, 1u);
+                            umma_bf16(d_tmem, adesc + 2 * stepA, bdesc + 2 * stepB, idesc, 1u);
+                            umma_bf16(d_tmem, adesc + 3 * stepA, bdesc + 3 * stepB, idesc, 1u);
+                        }
                         umma_commit(vempty(sv));
                     }
                     __syncwarp();
@@ -445,23 +462,28 @@ static int launch_wgrad_impl(const CUtensorMap& tz, const CUtensorMap& ts, const
     return B200_OK;
 }
 
-static int chunk_width(int C) {
-    if (C % 64 == 0) return 64;
-    if (C % 32 == 0) return 32;
-    if (C % 16 == 0) return 16;
+// widest channel chunk whose pixel row is 128 / 64 / 32 bytes
+static int chunk_width(int C, int esize) {
+    for (int bytes = 128; bytes >= 32; bytes >>= 1)
+        if (C % (bytes / esize) == 0) return bytes / esize;
     return 0;
 }
 
 // dw must be zero-initialised by the caller (partial sums of the reduction splits are added to it).
+// in_fp32: dz / src are fp32 tensors and the products are TF32 (see WgradParams::in_fp32).
 int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, int B, int H, int W,
-                    int ksize, float* dw, long long ldk, int koff, cudaStream_t stream) {
+                    int ksize, float* dw, long long ldk, int koff, cudaStream_t stream, int in_fp32) {
+    const int esize = in_fp32 ? 4 : 2;
+    const int rb_pixels = 128 / esize;   // pixels per pipeline stage: 64 (bf16) or 32 (fp32)
     WgradParams p = {};
+    p.in_fp32 = in_fp32;
     p.T = T; p.B = B; p.H = H; p.W = W;
     p.Nz = Nz; p.Csrc = Csrc; p.ksize = ksize; p.pad = ksize / 2; p.taps = ksize * ksize;
-    p.cwS = chunk_width(Nz);
-    p.cwV = chunk_width(Csrc);
+    p.cwS = chunk_width(Nz, esize);
+    p.cwV = chunk_width(Csrc, esize);
+    if (in_fp32 && (p.cwS != 32 || p.cwV != 32)) p.cwS = p.cwV = 0;   // tf32: 128-byte pixel rows only (32 channels)
     if (p.cwS == 0 || p.cwV == 0) {
-        set_last_error("wgrad_tc: channels Nz=%d Csrc=%d not multiples of 16", Nz, Csrc);
+        set_last_error("wgrad_tc: channels Nz=%d Csrc=%d not multiples of %d", Nz, Csrc, 32 / esize);
         return B200_ERR_SHAPE;
     }
     if ((ldk % 4) != 0 || (koff % 4) != 0) {
@@ -469,7 +491,7 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
         return B200_ERR_ALIGN;
     }
     MTile mt;
-    if (!plan_mtile(B, H, W, WG_RB, &mt)) {
+    if (!plan_mtile(B, H, W, rb_pixels, &mt)) {
         set_last_error("wgrad_tc: spatial shape B=%d H=%d W=%d cannot be tiled", B, H, W);
         return B200_ERR_SHAPE;
     }
@@ -477,7 +499,8 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     p.tiles_w = mt.tiles_w; p.tiles_h = mt.tiles_h; p.tiles_b = mt.tiles_b;
     p.num_rblocks = T * mt.tiles_w * mt.tiles_h * mt.tiles_b;
     // few source channels: stack G taps of the source along M, dz becomes the N operand
-    const bool stacked = (Csrc == 16 || Csrc == 32 || Csrc == 64) && p.taps > 1;
+    // (the stacked source box is ONE channel chunk: its pixel row must fit the 128-byte swizzle span)
+    const bool stacked = (Csrc * esize == 32 || Csrc * esize == 64 || Csrc * esize == 128) && p.taps > 1;
     int block_n;
     if (stacked) {
         p.G = WG_BLOCK_M / Csrc;
@@ -520,9 +543,9 @@ int launch_wgrad_tc(const void* dz, int Nz, const void* src, int Csrc, int T, in
     p.err_flag = device_error_flag();
 
     CUtensorMap tz, ts;
-    int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.cwS, mt.Wt, mt.Ht, mt.Bt);
+    int rc = make_act_tmap(&tz, dz, Nz, W, H, B, T, p.cwS, mt.Wt, mt.Ht, mt.Bt, esize, in_fp32);
     if (rc != B200_OK) return rc;
-    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.cwV, mt.Wt, mt.Ht, mt.Bt);
+    rc = make_act_tmap(&ts, src, Csrc, W, H, B, T, p.cwV, mt.Wt, mt.Ht, mt.Bt, esize, in_fp32);
     if (rc != B200_OK) return rc;
     if (stacked) {
         switch (block_n) {

@@ -331,7 +331,7 @@ class ConvLSTMSeq(torch.autograd.Function):
         h_all = torch.empty((T + 1, B, H, W, Ch), device=dev, dtype=dt)
         c_all = torch.empty((T + 1, B, H, W, Ch), device=dev, dtype=torch.float32)
         # gate recompute (ops.GATE_RECOMPUTE): the activated gates are not kept for backward
-        recompute = bool(fused and ops.GATE_RECOMPUTE and any(ctx.needs_input_grad))
+        recompute = bool(fused and dt == torch.bfloat16 and ops.GATE_RECOMPUTE and any(ctx.needs_input_grad))
         gates = None if recompute else torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
         have_h0 = h0 is not None
         if have_h0:
@@ -342,7 +342,7 @@ class ConvLSTMSeq(torch.autograd.Function):
             c_all[0].zero_()
         if fused:
             wp, bp = cache.get(("lstm", dt), (weight, bias), lambda: ops.pack_lstm_weight(weight, bias, dt))
-            if ops.PERSISTENT_LSTM:
+            if ops.PERSISTENT_LSTM and dt == torch.bfloat16:   # (the tf32 mode launches the fused cell per step)
                 ops.lstm_seq_fwd_fused(x_seq, h_all, c_all, wp, bp, gates, have_h0, ks)
             else:
                 for t in range(T):

@@ -21,9 +21,12 @@ _PRECISION = os.environ.get("B200_PRECISION", "bf16")
 
 def set_precision(mode: str) -> None:
     """'bf16': tcgen05 tensor-core path, bf16 activations, fp32 accumulation and cell state.
+    'tf32': fp32 activations and weights, convolutions and the fused cell forward on tcgen05 kind::tf32 (TF32 products,
+            fp32 accumulation: the arithmetic of the reference's own GPU runs, cuDNN with torch's default allow_tf32);
+            the weight-gradient reductions stay on the CUDA-core fp32 kernels.
     'fp32': check mode -- fp32 storage and CUDA-core FMA convolutions (1e-5 parity with the reference)."""
     global _PRECISION
-    if mode not in ("bf16", "fp32"):
+    if mode not in ("bf16", "tf32", "fp32"):
         raise ValueError(f"unknown precision mode {mode!r}")
     _PRECISION = mode
 
@@ -33,7 +36,7 @@ def get_precision() -> str:
 
 
 def act_dtype() -> torch.dtype:
-    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 
 
 # ------------------------------------------------------------------------------------------------
@@ -238,6 +241,11 @@ def conv_fwd(x0, x1, wp, bias, ksize, out0, out1=None, relu=False, bn_ws=None):
     tag = f"K{C0 + C1} N{N} {H}x{W} k{ksize}"
     work = (2.0 * T * B * H * W * ksize * ksize * (C0 + C1) * N, None)
     tc = tc_conv_ok(x0, x1, N) and split % 16 == 0 and out0.shape[-1] % 8 == 0 and ld1 % 8 == 0
+    if (not tc and _PRECISION == "tf32" and x0.dtype == torch.float32 and out0.dtype == torch.float32 and split % 16 == 0
+            and out0.shape[-1] % 4 == 0 and ld1 % 4 == 0 and _lib.supported("b200_conv_tf32_supported", B, H, W, C0, C1, N, 0)):
+        _lib.call("b200_conv_tf32_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(bias), N, ksize, _p(out0),
+                  out0.shape[-1], split, _p(out1), ld1, int(relu), 0, _st(), tag=tag + " tf32", work=work)
+        return False
     if tc and bn_ws is not None and out1 is None and not relu and out0.dtype == torch.bfloat16:
         _lib.call("b200_conv_bnstats_tc_fwd", _p(x0), C0, _p(x1), C1, T, B, H, W, _p(wp), _p(bias), N, ksize,
                   _p(out0), _p(bn_ws[0]), _p(bn_ws[1]), _st(), tag=tag + " +bnstats", work=work)
@@ -295,6 +303,10 @@ def conv_wgrad(dz, src, ksize, dw, koff):
             _lib.supported("b200_wgrad_tc_supported", B, H, W, Nz, Cs):
         _lib.call("b200_wgrad_tc", _p(dz), Nz, _p(src), Cs, T, B, H, W, ksize, _p(dw), ldk, koff, _st(),
                   tag=tag, work=work)
+    elif (_PRECISION == "tf32" and WGRAD_TF32 and dz.dtype == torch.float32 and src.dtype == torch.float32 and ldk % 4 == 0
+          and koff % 4 == 0 and _lib.supported("b200_wgrad_tf32_supported", B, H, W, Nz, Cs)):
+        _lib.call("b200_wgrad_tf32", _p(dz), Nz, _p(src), Cs, T, B, H, W, ksize, _p(dw), ldk, koff, _st(),
+                  tag=tag + " tf32", work=work)
     else:
         _lib.call("b200_wgrad_simt", _p(dz), Nz, _p(src), Cs, T * B, H, W, ksize, _p(dw), ldk, koff, _f32(dz), _st(),
                   tag=tag, work=work)
@@ -457,11 +469,16 @@ def outconv_bwd(x, w, dy, need_dx=True):
 # ConvLSTM cell
 # ------------------------------------------------------------------------------------------------
 def lstm_tc_ok(x_t, Ch) -> bool:
+    B, H, W, Cin = x_t.shape
+    if x_t.dtype == torch.float32 and _PRECISION == "tf32":
+        return _lib.supported("b200_conv_tf32_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
     if x_t.dtype != torch.bfloat16:
         return False
-    B, H, W, Cin = x_t.shape
     return _lib.supported("b200_conv_tc_supported", B, H, W, Cin, Ch, 4 * Ch, 1)
 
+
+# tf32 mode: weight gradients on tcgen05 kind::tf32 (1) or on the CUDA-core fp32 kernel (0)
+WGRAD_TF32 = os.environ.get("B200_WGRAD_TF32", "1") != "0"
 
 # ConvTranspose 2x2: pixel shuffle in the GEMM epilogue (1) or GEMM + separate shuffle kernel (0)
 CONVT_FUSED = os.environ.get("B200_CONVT_FUSED", "1") != "0"
@@ -658,7 +675,8 @@ def lstm_cell_fwd_fused(x_t, h_prev, c_prev, wp_il, bias_il, c_next, h_next, gat
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
     kin_ = Cin + (Ch if h_prev is not None else 0)
-    _lib.call("b200_convlstm_cell_fwd_tc", _p(x_t), Cin, _p(h_prev), Ch, B, H, W, _p(wp_il), _p(bias_il),
+    entry = "b200_convlstm_cell_fwd_tf32" if x_t.dtype == torch.float32 else "b200_convlstm_cell_fwd_tc"
+    _lib.call(entry, _p(x_t), Cin, _p(h_prev), Ch, B, H, W, _p(wp_il), _p(bias_il),
               _p(c_prev), _p(c_next), _p(h_next), _p(gates), ksize, _st(), tag=f"Ch{Ch} {H}x{W}",
               work=(2.0 * B * H * W * ksize * ksize * kin_ * 4 * Ch, None))
     if timer is not None:
