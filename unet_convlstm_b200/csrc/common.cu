@@ -225,7 +225,7 @@ int make_tmap_5d(CUtensorMap* out, const void* base, const uint64_t dims[5],
             return B200_ERR_ALIGN;
         }
     }
-    CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+    CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
                     const_cast<void*>(base), gdim, gstr, bx,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     // atom32: the 128-byte swizzle on 32-byte atoms (4-row period) -- what an MN-major operand of 32-bit
@@ -274,7 +274,7 @@ int make_w_tmap(CUtensorMap* out, const void* base, int K, int rows, int taps, i
     cuuint64_t gstr[2] = {cuuint64_t(K) * esize, cuuint64_t(K) * esize * rows};
     cuuint32_t bx[3] = {cuuint32_t(box_k), cuuint32_t(box_rows), 1u};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+    CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                     const_cast<void*>(base), gdim, gstr, bx,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_k * esize),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

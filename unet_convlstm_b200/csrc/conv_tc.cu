@@ -615,12 +615,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                                 zg += __ldg(bp + 2 * CHT + j);
                                 zo += __ldg(bp + 3 * CHT + j);
                             }
-                            gi[j] = fast_sigmoid(zi);
-                            gf[j] = fast_sigmoid(zf);
-                            gg[j] = fast_tanh(zg);
-                            go[j] = fast_sigmoid(zo);
-                            cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
-                            hn[j] = go[j] * fast_tanh(cn[j]);
+                            if (p.state_fp32) {
+                                // tf32 mode: full-precision gate functions.  The BPTT derivative s(1-s) is formed from
+                                // the stored gate, so an absolute error of 2^-12 (tanh.approx) in a saturated gate is a
+                                // relative error of percents in its gradient -- fine next to bf16 storage, not here.
+                                gi[j] = 1.f / (1.f + expf(-zi));
+                                gf[j] = 1.f / (1.f + expf(-zf));
+                                gg[j] = tanhf(zg);
+                                go[j] = 1.f / (1.f + expf(-zo));
+                                cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
+                                hn[j] = go[j] * tanhf(cn[j]);
+                            } else {
+                                gi[j] = fast_sigmoid(zi);
+                                gf[j] = fast_sigmoid(zf);
+                                gg[j] = fast_tanh(zg);
+                                go[j] = fast_sigmoid(zo);
+                                cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
+                                hn[j] = go[j] * fast_tanh(cn[j]);
+                            }
                         }
                         if (p.c_next) {
                             float4* co = reinterpret_cast<float4*>(p.c_next + coff);
