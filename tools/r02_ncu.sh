@@ -8,9 +8,9 @@ CMD="python bench.py --profile-steps 1 --no-cpu-baseline"
 $CMD > gpurun_out/plain_prof.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"conv_tc2_kernel<256, 1>" -s 3 -c 1 -f -o gpurun_out/r02_prof_cell $CMD > gpurun_out/ncu_cell.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"conv_tc2_kernel<.int.256, .int.1>" -s 3 -c 1 -f -o gpurun_out/r02_prof_cell $CMD > gpurun_out/ncu_cell.log 2>&1
 echo "cell rc=$?"
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"wgrad_tc2_kernel<256" -s 20 -c 2 -f -o gpurun_out/r02_prof_wgrad2 $CMD > gpurun_out/ncu_wgrad2.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"wgrad_tc2_kernel<.int.256" -s 20 -c 2 -f -o gpurun_out/r02_prof_wgrad2 $CMD > gpurun_out/ncu_wgrad2.log 2>&1
 echo "wgrad2 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"wgrad_tc_kernel" -s 4 -c 2 -f -o gpurun_out/r02_prof_wgrad1 $CMD > gpurun_out/ncu_wgrad1.log 2>&1
 echo "wgrad1 rc=$?"
