@@ -185,6 +185,21 @@ int b200_maxpool2_fwd(const void* x, void* y, long long IMG, int H, int W, int C
 int b200_maxpool2_bwd(const void* x, const void* dy, void* dx, long long IMG, int H, int W, int C,
                       int accumulate, int dtype_fp32, void* stream);
 
+/* BatchNorm2d + ReLU + MaxPool2d(2) in one pass for a DoubleConv output that feeds both a skip connection and the
+ * next Down stage (unet.py:70-71 -> :81, :179-182): y = relu(x*scale+shift) [T][B][H][W][C] and pooled = maxpool2x2(y)
+ * [T][B][H/2][W/2][C].  H and W even.  The backward pair takes the two gradients of y -- dy through the skip connection
+ * (may be NULL) and dp through the pool -- and replaces b200_maxpool2_bwd + b200_bn_relu_bwd_reduce / _apply; results
+ * are bit-identical to the separate entry points. */
+int b200_bn_relu_apply_pool(const void* x, const float* scale, const float* shift, void* y, void* pooled, int T,
+                            long long B, int H, int W, int C, int tstride, int dtype_fp32, void* stream);
+int b200_bn_relu_pool_bwd_reduce(const void* x, const void* dy, const void* dp, const float* mean, const float* rstd,
+                                 const float* scale, const float* shift, int T, long long B, int H, int W, int C,
+                                 int tstride, int dtype_fp32, double* sum_g, double* sum_gx, void* stream);
+int b200_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp, const float* mean, const float* rstd,
+                                const float* scale, const float* shift, const float* coef1, const float* coef2,
+                                void* dx, int T, long long B, int H, int W, int C, int tstride, int dtype_fp32,
+                                void* stream);
+
 /* ConvLSTM gate math when it is not fused into the GEMM epilogue (unet.py:29-35).  z: fp32 [P][4*Ch]
  * pre-activations in the reference's chunk order i|f|g|o; gates: [P][4][Ch] activated. */
 int b200_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next,

@@ -1061,3 +1061,90 @@ def test_convlstm_other_kernel_sizes(ks, cin, ch):
             assert rel2(_np(m.layers[0].conv.bias.grad), b.grad.numpy()) < tol_g, mode
     finally:
         pkg.set_precision("bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm + ReLU + 2x2 max-pool in one pass (encoder outputs: skip connection + next Down stage)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 2, 8, 12, 16), (2, 3, 6, 4, 24), (2, 2, 4, 4, 7), (1, 1, 2, 2, 64)])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_relu_pool_fused_matches_separate_kernels(mode, shape, training):
+    """b200_bn_relu_apply_pool / b200_bn_relu_pool_bwd_reduce / _apply against b200_bn_relu_apply + b200_maxpool2_fwd and
+    b200_maxpool2_bwd (accumulating into the skip gradient) + b200_bn_relu_bwd_reduce / _apply: the forward outputs and
+    the gradient that reaches the BatchNorm backward are bit-identical by construction; the fp64 sums are accumulated in
+    a different order, so dz / dgamma / dbeta agree to rounding.  Vector (C % 8 == 0) and scalar channel counts, ties
+    (whole windows clamped to zero by the ReLU), with and without a skip gradient."""
+    from unet_convlstm_b200 import ops
+    T, B, H, W, C = shape
+    dt = ops.act_dtype()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.randn(shape, device="cuda", generator=g).to(dt)
+    z[:, :, : H // 2, : W // 2] -= 3.0      # a quadrant where most windows are all-zero after the ReLU (ties)
+    gamma = (0.5 + torch.rand(C, device="cuda", generator=g))
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    dy = torch.randn(shape, device="cuda", generator=g).to(dt)
+    dp = torch.randn((T, B, H // 2, W // 2, C), device="cuda", generator=g).to(dt)
+
+    def stats():
+        rm = torch.zeros(C, device="cuda")
+        rv = torch.ones(C, device="cuda")
+        return rm, rv
+
+    rm, rv = stats()
+    (y1, p1), st1 = ops.bn_relu_fwd(z, gamma, beta, rm, rv, training, 1e-5, 0.1, pool=True)
+    rm2, rv2 = stats()
+    y0, st0 = ops.bn_relu_fwd(z, gamma, beta, rm2, rv2, training, 1e-5, 0.1)
+    p0 = ops.maxpool2_fwd(y0)
+    assert torch.equal(y1, y0) and torch.equal(p1, p0)
+    assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
+
+    for skip in (True, False):
+        g0 = ops.maxpool2_bwd(y0, dp, accumulate_into=dy.clone()) if skip else ops.maxpool2_bwd(y0, dp)
+        dz0, dg0, db0, dc0 = ops.bn_relu_bwd(z, g0, st0, training, True)
+        dz1, dg1, db1, dc1 = ops.bn_relu_bwd(z, dy if skip else None, st1, training, True, dpool=dp)
+        tol = 1e-5 if mode == "fp32" else 6e-3     # bf16: an occasional last-bit difference of the stored dz
+        assert rel(_np(dz1), _np(dz0)) < tol, (skip, rel(_np(dz1), _np(dz0)))
+        assert rel2(_np(dz1), _np(dz0)) < (1e-6 if mode == "fp32" else 1e-3)
+        for a, b in ((dg1, dg0), (db1, db0), (dc1, dc0)):
+            assert np.abs(_np(a) - _np(b)).max() <= 1e-5 * max(np.abs(_np(b)).max(), 1.0)
+
+
+@pytest.mark.parametrize("size", [(16, 16), (20, 12)])
+def test_model_fused_pool_matches_pool_fork(mode, size):
+    """TemporalUNetDualView with the fused BatchNorm/ReLU/max-pool passes against the same model on the separate kernels
+    (ops.FUSE_BN_POOL off -> PoolFork): outputs bit-identical, every parameter gradient equal to summation-order noise
+    (20x12 has odd sizes from the third level down: those stages fall back to PoolFork by themselves)."""
+    from train.unet import TemporalUNetDualView
+    from unet_convlstm_b200 import ops
+    H, W = size
+    torch.manual_seed(3)
+    m = TemporalUNetDualView(base_ch=8, use_skip_lstm=True).cuda()
+    x = torch.randn(2, 3, 2, H, W, device="cuda")
+    w = torch.randn(3, 2, 1, H, W, device="cuda")
+    res = []
+    old = ops.FUSE_BN_POOL
+    try:
+        for fuse in (True, False):
+            ops.FUSE_BN_POOL = fuse
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            m.zero_grad(set_to_none=True)
+            n0 = dict(__import__("unet_convlstm_b200")._lib.CALLS)
+            out, _ = m(x)
+            y = torch.stack(out, 0)
+            (y * w).sum().backward()
+            calls = {k: v - n0.get(k, 0) for k, v in __import__("unet_convlstm_b200")._lib.CALLS.items()}
+            res.append((y.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()},
+                        {k: v.clone() for k, v in m.state_dict().items()}, calls))
+            m.load_state_dict(sd)
+    finally:
+        ops.FUSE_BN_POOL = old
+    (y1, g1, s1, c1), (y0, g0, s0, c0) = res
+    assert c1.get("b200_bn_relu_apply_pool", 0) >= 2 and c1.get("b200_bn_relu_pool_bwd_apply", 0) >= 2
+    assert c0.get("b200_bn_relu_apply_pool", 0) == 0 and c0.get("b200_maxpool2_bwd", 0) == 4
+    assert torch.equal(y1, y0)
+    for k in s0:
+        assert torch.equal(s1[k], s0[k]), k
+    for k in g0:
+        a, b = _np(g1[k]), _np(g0[k])
+        scale = max(np.abs(b).max(), 1e-6)
+        assert np.abs(a - b).max() <= (1e-4 if mode == "fp32" else 3e-2) * scale, (k, np.abs(a - b).max() / scale)

@@ -122,7 +122,9 @@ class DoubleConv(nn.Module):
             nn.Conv2d(out_ch, out_ch, 3, padding=1), nn.BatchNorm2d(out_ch), nn.ReLU(inplace=True))
         self._caches = (Fn.WeightCache(), Fn.WeightCache())
 
-    def _half(self, i, x0, x1):
+    def _half(self, i, x0, x1, pool=False):
+        """One conv + BatchNorm + ReLU.  pool: returns (y, maxpool2x2(y)) -- the skip tensor and the input of the next
+        Down stage -- from one normalise pass when the fused kernels apply, from a separate max-pool otherwise."""
         conv, bn = self.net[3 * i], self.net[3 * i + 1]
         T = x0.shape[0]
         training = self.training or not bn.track_running_stats
@@ -137,22 +139,24 @@ class DoubleConv(nn.Module):
                 ("bn_eval",), (bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.bias),
                 lambda: ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                                 bn.eps, conv.bias))
-            return ops.conv_affine_relu(Fn._c(x0), None if x1 is None else Fn._c(x1), wp, scale, shift,
-                                        conv.kernel_size[0])
+            y = ops.conv_affine_relu(Fn._c(x0), None if x1 is None else Fn._c(x1), wp, scale, shift,
+                                     conv.kernel_size[0])
+            return Fn.PoolFork.apply(y) if pool else y
         # momentum=None is torch's cumulative moving average (factor 1 / num_batches_tracked): encoded for the finalize
         # kernel as -(n0 + 1), n0 = the count before this call (one BatchNorm call per timestep, so step t uses n0 + t + 1)
         if bn.momentum is not None:
             momentum = float(bn.momentum)
         else:
             momentum = -(float(bn.num_batches_tracked) + 1.0) if bn.track_running_stats else 0.0
+        fuse_pool = pool and ops.bn_pool_ok(x0)
         y = Fn.ConvBnRelu.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                training, bn.eps, momentum, self._caches[i])
+                                training, bn.eps, momentum, self._caches[i], fuse_pool)
         if training and bn.track_running_stats:
             bn.num_batches_tracked += T  # one BatchNorm call per timestep in the reference
-        return y
+        return Fn.PoolFork.apply(y) if (pool and not fuse_pool) else y
 
-    def _seq(self, x0, x1=None):
-        return self._half(1, self._half(0, x0, x1), None)
+    def _seq(self, x0, x1=None, pool=False):
+        return self._half(1, self._half(0, x0, x1), None, pool)
 
     def forward(self, x):
         _require_cuda(x, "DoubleConv")
@@ -167,10 +171,9 @@ class Down(nn.Module):
     def _seq(self, x):
         return self.net[1]._seq(Fn.MaxPool2.apply(x))
 
-    def _seq_fork(self, x):
-        """(x for the skip connection, Down(x)): the two gradients of x are summed inside the max-pool backward."""
-        skip, pooled = Fn.PoolFork.apply(x)
-        return skip, self.net[1]._seq(pooled)
+    def _seq_pooled(self, pooled, pool=False):
+        """The DoubleConv of this stage on an input the previous stage already pooled (DoubleConv._seq(pool=True))."""
+        return self.net[1]._seq(pooled, None, pool)
 
     def forward(self, x):
         _require_cuda(x, "Down")
@@ -248,11 +251,13 @@ class TemporalUNetDualView(nn.Module):
         self.outc = OutConv(b, out_channels)
 
     def _encode(self, x):
-        x0 = self.inc._seq(x)
-        x0, x1 = self.down1._seq_fork(x0)
-        x1, x2 = self.down2._seq_fork(x1)
-        x2, x3 = self.down3._seq_fork(x2)
-        x3, xb = self.bottleneck._seq_fork(x3)
+        # every encoder output feeds a skip connection and the max-pool of the next stage: the stage that produces it
+        # also pools it (one pass; the two gradients meet inside its BatchNorm backward)
+        x0, p0 = self.inc._seq(x, None, True)
+        x1, p1 = self.down1._seq_pooled(p0, True)
+        x2, p2 = self.down2._seq_pooled(p1, True)
+        x3, p3 = self.down3._seq_pooled(p2, True)
+        xb = self.bottleneck._seq_pooled(p3)
         if self.use_attention:
             T, B, H, W, C = xb.shape
             a = self.attention(xb.reshape(T * B, H, W, C).permute(0, 3, 1, 2).float())

@@ -473,6 +473,46 @@ extern "C" int b200_maxpool2_bwd(const void* x, const void* dy, void* dx, long l
     return launch_maxpool2_bwd(x, dy, dx, IMG, H, W, C, accumulate, dtype_fp32, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int b200_bn_relu_apply_pool(const void* x, const float* scale, const float* shift, void* y, void* pooled,
+                                       int T, long long B, int H, int W, int C, int tstride, int dtype_fp32,
+                                       void* stream) {
+    B200_REQUIRE(x && scale && shift && y && pooled && T > 0 && B > 0 && H > 0 && W > 0 && C > 0, "b200_bn_relu_apply_pool");
+    if ((H & 1) || (W & 1)) {
+        set_last_error("b200_bn_relu_apply_pool: H and W must be even (got %dx%d)", H, W);
+        return B200_ERR_SHAPE;
+    }
+    return launch_bn_relu_apply_pool(x, scale, shift, y, pooled, T, B, H, W, C, tstride, dtype_fp32,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_pool_bwd_reduce(const void* x, const void* dy, const void* dp, const float* mean,
+                                            const float* rstd, const float* scale, const float* shift, int T,
+                                            long long B, int H, int W, int C, int tstride, int dtype_fp32,
+                                            double* sum_g, double* sum_gx, void* stream) {
+    B200_REQUIRE(x && dp && mean && rstd && scale && shift && sum_g && sum_gx && T > 0 && B > 0 && H > 0 && W > 0 && C > 0,
+                 "b200_bn_relu_pool_bwd_reduce");
+    if ((H & 1) || (W & 1)) {
+        set_last_error("b200_bn_relu_pool_bwd_reduce: H and W must be even (got %dx%d)", H, W);
+        return B200_ERR_SHAPE;
+    }
+    return launch_bn_relu_pool_bwd_reduce(x, dy, dp, mean, rstd, scale, shift, T, B, H, W, C, tstride, dtype_fp32, sum_g,
+                                          sum_gx, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp, const float* mean,
+                                           const float* rstd, const float* scale, const float* shift,
+                                           const float* coef1, const float* coef2, void* dx, int T, long long B, int H,
+                                           int W, int C, int tstride, int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && dp && mean && rstd && scale && shift && coef1 && coef2 && dx && T > 0 && B > 0 && H > 0 && W > 0 && C > 0,
+                 "b200_bn_relu_pool_bwd_apply");
+    if ((H & 1) || (W & 1)) {
+        set_last_error("b200_bn_relu_pool_bwd_apply: H and W must be even (got %dx%d)", H, W);
+        return B200_ERR_SHAPE;
+    }
+    return launch_bn_relu_pool_bwd_apply(x, dy, dp, mean, rstd, scale, shift, coef1, coef2, dx, T, B, H, W, C, tstride,
+                                         dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next,
                                    long long P, int Ch, int dtype_fp32, void* stream) {
     B200_REQUIRE(z && gates && c_next && h_next && P > 0 && Ch > 0, "b200_lstm_gates_fwd");

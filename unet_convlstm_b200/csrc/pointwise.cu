@@ -140,11 +140,18 @@ struct ReduceGeom {
 };
 
 // Op::load(frag, t, row, c) fetches the raw operands of V channels starting at c of one row;
-// Op::accum(state, frag, a0, a1) adds their contribution.  The row loop loads COLRED_U rows ahead.
-static constexpr int COLRED_U = 4;
+// Op::accum(state, frag, a0, a1) adds their contribution.  The row loop loads ColredTraits<Op>::U rows ahead;
+// ColredTraits<Op>::BLOCKS = resident blocks per SM the bf16 instantiation is compiled for (an Op whose "row" is a
+// 2x2 pixel window holds nine 16-byte vectors per row: one row in flight, two blocks per SM).
+template <typename Op>
+struct ColredTraits {
+    static constexpr int U = 4;
+    static constexpr int BLOCKS = 4;
+};
 template <typename T, int V, typename Acc, typename Op>
-__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : 4)) colreduce_kernel(const Op op, const ReduceGeom g, double* __restrict__ out0,
+__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : ColredTraits<Op>::BLOCKS)) colreduce_kernel(const Op op, const ReduceGeom g, double* __restrict__ out0,
                                                         double* __restrict__ out1) {
+    constexpr int COLRED_U = ColredTraits<Op>::U;
     __shared__ Acc red[2][256 * (V > 4 ? 4 : V)];  // reduced in two halves when V == 8
     const int tid = threadIdx.x;
     const int r = tid / g.cvb;
@@ -220,7 +227,7 @@ static int launch_colreduce(const Op& op, int T_, long long P, int C, int V, dou
     // at most 8 blocks per SM in total (= two full waves at 4 resident blocks per SM; rounding UP here gave 1200 blocks
     // on 1184 slots at T = 20, i.e. a third, almost empty wave: ncu showed the SMs idle for 21 % of the kernel), at
     // least 4 iterations per thread
-    long long want_x = (8LL * num_sms()) / ((long long)gy * T_);
+    long long want_x = (2LL * ColredTraits<Op>::BLOCKS * num_sms()) / ((long long)gy * T_);
     long long max_x = (P + 4LL * g.rows_per_iter - 1) / (4LL * g.rows_per_iter);
     if (want_x > max_x) want_x = max_x;
     if (want_x < 1) want_x = 1;
@@ -819,6 +826,326 @@ int launch_maxpool2_bwd(const void* x, const void* dy, void* dx, long long IMG, 
         go(float(), pick_vec<float>(C, {x, dy, dx}));
     else
         go(__nv_bfloat16(), pick_vec<__nv_bfloat16>(C, {x, dy, dx}));
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU + 2x2 max-pool in ONE pass, forward and backward: the DoubleConv output of an encoder stage
+// feeds a skip connection AND the MaxPool2d of the next Down (unet.py:70-71, 81, 179-182).  Separately that is
+// apply (read z, write y) + pool (read y, write pooled) forward and pool-backward (read y, g_skip, g_pool, write g) +
+// BatchNorm-backward sums (read z, g) + apply (read z, g, write dz) backward: 3.25 + 8.25 passes over the full-size
+// tensor; fused it is 2.25 + 5.5.  A "row" of the row loop is one 2x2 window (H and W even; the host falls back to
+// the separate kernels otherwise).  Results are bit-identical to the separate kernels: the maximum is taken over
+// the values as they are STORED (rounded to T), ties go to the first pixel in scan order (ATen
+// max_pool2d_with_indices), and the summed gradient g_skip + routed g_pool is rounded to T like the stored one was.
+// ------------------------------------------------------------------------------------------------
+struct WinGeom {
+    int H, W, Ho, Wo;  // Ho = H / 2, Wo = W / 2
+    long long P;       // pixels per timestep = B * H * W
+    long long Pw;      // windows per timestep = B * Ho * Wo
+    int C;
+};
+
+// window w of a timestep -> index of its top-left pixel inside that timestep
+__device__ __forceinline__ long long win_pixel(long long w, const WinGeom& q) {
+    const long long r = w / q.Wo;
+    const int wo = static_cast<int>(w - r * q.Wo);
+    const long long b = r / q.Ho;
+    const int ho = static_cast<int>(r - b * q.Ho);
+    return (b * q.H + 2 * ho) * q.W + 2 * wo;
+}
+
+// v as a store to T rounds it
+template <typename T>
+__device__ __forceinline__ float as_stored(float v) {
+    if constexpr (std::is_same<T, float>::value)
+        return v;
+    else
+        return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_relu_apply_pool_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, T* __restrict__ y,
+                                                                 T* __restrict__ pooled, const ReduceGeom g,
+                                                                 const WinGeom q, int tstride) {
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;
+    const int cv = tid - r * g.cvb;
+    const int c = (blockIdx.y * g.cvb + cv) * V;
+    const int t = blockIdx.z;
+    if (r >= g.rows_per_iter || c >= g.C) return;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = __ldg(scale + t * tstride + c + j);
+        sh[j] = __ldg(shift + t * tstride + c + j);
+    }
+    const long long w_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long w_end = w_begin + g.rows_per_block;
+    if (w_end > g.P) w_end = g.P;
+    const long long base = static_cast<long long>(t) * q.P;
+    const long long wbase = static_cast<long long>(t) * q.Pw;
+    const long long dk[4] = {0, q.C, static_cast<long long>(q.W) * q.C, static_cast<long long>(q.W + 1) * q.C};
+#pragma unroll 2
+    for (long long w = w_begin + r; w < w_end; w += g.rows_per_iter) {
+        const long long off = (base + win_pixel(w, q)) * q.C + c;
+        RawVec<T, V> rx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ld_raw<T, V>(x + off + dk[k], rx[k]);
+        float m[V];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[V];
+            unpack_raw<T, V>(rx[k], f);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                m[j] = k == 0 ? f[j] : fmaxf(m[j], f[j]);  // rounding is monotonic: max of the stored = stored max
+            }
+            stv<T, V>(y + off + dk[k], f);
+        }
+        stv<T, V>(pooled + (wbase + w) * q.C + c, m);
+    }
+}
+
+static WinGeom win_geom(long long B, int H, int W, int C) {
+    WinGeom q;
+    q.H = H; q.W = W; q.Ho = H / 2; q.Wo = W / 2;
+    q.P = B * H * W;
+    q.Pw = B * q.Ho * q.Wo;
+    q.C = C;
+    return q;
+}
+
+int launch_bn_relu_apply_pool(const void* x, const float* scale, const float* shift, void* y, void* pooled, int T_,
+                              long long B, int H, int W, int C, int tstride, int dtype_fp32, cudaStream_t stream) {
+    const WinGeom q = win_geom(B, H, W, C);
+    auto go = [&](auto tag, int V) {
+        using T = decltype(tag);
+        dim3 grid;
+        const ReduceGeom g = rowloop_geom(T_, q.Pw, C, V, &grid);
+        const T* xs = static_cast<const T*>(x);
+        T* ys = static_cast<T*>(y);
+        T* ps = static_cast<T*>(pooled);
+        if (V == 1)
+            bn_relu_apply_pool_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, ps, g, q, tstride);
+        else if constexpr (std::is_same<T, float>::value)
+            bn_relu_apply_pool_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, ps, g, q, tstride);
+        else
+            bn_relu_apply_pool_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, scale, shift, ys, ps, g, q, tstride);
+    };
+    if (dtype_fp32)
+        go(float(), pick_vec<float>(C, {x, y, pooled}));
+    else
+        go(__nv_bfloat16(), pick_vec<__nv_bfloat16>(C, {x, y, pooled}));
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+// The gradient that reaches the ReLU output of the four pixels of a window: g_k = stored(g_skip_k + [k == argmax] g_pool)
+// (g_skip may be absent).  arg[] is found on the stored activations, exactly as maxpool2_bwd_kernel finds it on y.
+// Returns the argmax of channel j in bits [2j, 2j+2).
+template <typename T, int V>
+__device__ __forceinline__ unsigned window_argmax(const RawVec<T, V> (&rx)[4], const float (&sc)[V], const float (&sh)[V]) {
+    float best[V];
+    int arg[V];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float f[V];
+        unpack_raw<T, V>(rx[k], f);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float yv = as_stored<T>(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f));
+            if (k == 0) {
+                best[j] = yv;
+                arg[j] = 0;
+            } else if (yv > best[j]) {
+                best[j] = yv;
+                arg[j] = k;
+            }
+        }
+    }
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) bits |= static_cast<unsigned>(arg[j]) << (2 * j);
+    return bits;
+}
+
+struct BnBwdReducePoolOp {
+    const void* x;    // pre-BN conv output [T][P][C]
+    const void* dy;   // gradient w.r.t. the ReLU output through the skip connection, or nullptr
+    const void* dp;   // gradient w.r.t. the pooled output [T][Pw][C]
+    const float* mean;
+    const float* rstd;
+    const float* scale;
+    const float* shift;
+    WinGeom q;
+    int tstride;
+    template <int V>
+    struct State {
+        float sc[V], sh[V];
+    };
+    template <int V>
+    __device__ __forceinline__ void init(int t, int c, State<V>& st) const {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int i = t * tstride + c + j;
+            st.sc[j] = __ldg(scale + i);
+            st.sh[j] = __ldg(shift + i);
+        }
+    }
+    __device__ __forceinline__ void post(int t, int c, double& s0, double& s1) const {
+        const int i = t * tstride + c;
+        s1 = static_cast<double>(__ldg(rstd + i)) * (s1 - static_cast<double>(__ldg(mean + i)) * s0);
+    }
+    template <typename T, int V>
+    struct Frag {
+        RawVec<T, V> x[4], d[4], p;
+    };
+    template <typename T, int V>
+    __device__ __forceinline__ void load(Frag<T, V>& fr, int t, long long w, int c) const {
+        const long long off = (static_cast<long long>(t) * q.P + win_pixel(w, q)) * q.C + c;
+        const long long dk[4] = {0, q.C, static_cast<long long>(q.W) * q.C, static_cast<long long>(q.W + 1) * q.C};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ld_raw<T, V>(static_cast<const T*>(x) + off + dk[k], fr.x[k]);
+            if (dy) {
+                ld_raw<T, V>(static_cast<const T*>(dy) + off + dk[k], fr.d[k]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < RawVec<T, V>::NW; ++i) fr.d[k].w[i] = 0u;
+            }
+        }
+        ld_raw<T, V>(static_cast<const T*>(dp) + (static_cast<long long>(t) * q.Pw + w) * q.C + c, fr.p);
+    }
+    template <typename T, int V, typename Acc>
+    __device__ __forceinline__ void accum(const State<V>& st, const Frag<T, V>& fr, Acc (&a0)[V], Acc (&a1)[V]) const {
+        const unsigned arg = window_argmax<T, V>(fr.x, st.sc, st.sh);
+        float fp[V];
+        unpack_raw<T, V>(fr.p, fp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float fx[V], fd[V];
+            unpack_raw<T, V>(fr.x[k], fx);
+            unpack_raw<T, V>(fr.d[k], fd);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float gk = as_stored<T>(fd[j] + (((arg >> (2 * j)) & 3u) == static_cast<unsigned>(k) ? fp[j] : 0.f));
+                const float yv = fmaf(fx[j], st.sc[j], st.sh[j]);
+                const float gq = yv > 0.f ? gk : 0.f;
+                a0[j] += Acc(gq);
+                a1[j] += Acc(gq) * Acc(fx[j]);
+            }
+        }
+    }
+};
+template <>
+struct ColredTraits<BnBwdReducePoolOp> {
+    static constexpr int U = 1;
+    static constexpr int BLOCKS = 2;
+};
+
+int launch_bn_relu_pool_bwd_reduce(const void* x, const void* dy, const void* dp, const float* mean, const float* rstd,
+                                   const float* scale, const float* shift, int T_, long long B, int H, int W, int C,
+                                   int tstride, int dtype_fp32, double* sum_g, double* sum_gx, cudaStream_t stream) {
+    B200_CUDA_CHECK(cudaMemsetAsync(sum_g, 0, sizeof(double) * T_ * C, stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(sum_gx, 0, sizeof(double) * T_ * C, stream));
+    BnBwdReducePoolOp op{x, dy, dp, mean, rstd, scale, shift, win_geom(B, H, W, C), tstride};
+    if (dtype_fp32)
+        return launch_colreduce<float>(op, T_, op.q.Pw, C, pick_vec<float>(C, {x, dy, dp}), sum_g, sum_gx, stream);
+    return launch_colreduce<__nv_bfloat16>(op, T_, op.q.Pw, C, pick_vec<__nv_bfloat16>(C, {x, dy, dp}), sum_g, sum_gx, stream);
+}
+
+// dz of the four pixels of each window: dx = scale * g + ka * x + kb as in bn_relu_bwd_apply_kernel
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 2)
+bn_relu_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ dp,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              const float* __restrict__ scale, const float* __restrict__ shift,
+                              const float* __restrict__ coef1, const float* __restrict__ coef2, T* __restrict__ dx,
+                              const ReduceGeom g, const WinGeom q, int tstride) {
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;
+    const int cv = tid - r * g.cvb;
+    const int c = (blockIdx.y * g.cvb + cv) * V;
+    const int t = blockIdx.z;
+    if (r >= g.rows_per_iter || c >= g.C) return;
+    float sc[V], sh[V], ka[V], kb[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int ps = t * tstride + c + j, pc = t * g.C + c + j;
+        sc[j] = __ldg(scale + ps);
+        sh[j] = __ldg(shift + ps);
+        const float rc2 = __ldg(rstd + ps) * __ldg(coef2 + pc);
+        ka[j] = -sc[j] * rc2;
+        kb[j] = sc[j] * (rc2 * __ldg(mean + ps) - __ldg(coef1 + pc));
+    }
+    const long long w_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long w_end = w_begin + g.rows_per_block;
+    if (w_end > g.P) w_end = g.P;
+    const long long base = static_cast<long long>(t) * q.P;
+    const long long wbase = static_cast<long long>(t) * q.Pw;
+    const long long dk[4] = {0, q.C, static_cast<long long>(q.W) * q.C, static_cast<long long>(q.W + 1) * q.C};
+    for (long long w = w_begin + r; w < w_end; w += g.rows_per_iter) {
+        const long long off = (base + win_pixel(w, q)) * q.C + c;
+        RawVec<T, V> rx[4], rd[4], rp;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ld_raw<T, V>(x + off + dk[k], rx[k]);
+            if (dy) {
+                ld_raw<T, V>(dy + off + dk[k], rd[k]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < RawVec<T, V>::NW; ++i) rd[k].w[i] = 0u;
+            }
+        }
+        ld_raw<T, V>(dp + (wbase + w) * q.C + c, rp);
+        const unsigned arg = window_argmax<T, V>(rx, sc, sh);
+        float fp[V];
+        unpack_raw<T, V>(rp, fp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float fx[V], fd[V];
+            unpack_raw<T, V>(rx[k], fx);
+            unpack_raw<T, V>(rd[k], fd);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float gk = as_stored<T>(fd[j] + (((arg >> (2 * j)) & 3u) == static_cast<unsigned>(k) ? fp[j] : 0.f));
+                const float yv = fmaf(fx[j], sc[j], sh[j]);
+                const float gq = yv > 0.f ? gk : 0.f;
+                fd[j] = fmaf(sc[j], gq, fmaf(ka[j], fx[j], kb[j]));
+            }
+            stv<T, V>(dx + off + dk[k], fd);
+        }
+    }
+}
+
+int launch_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp, const float* mean, const float* rstd,
+                                  const float* scale, const float* shift, const float* coef1, const float* coef2,
+                                  void* dx, int T_, long long B, int H, int W, int C, int tstride, int dtype_fp32,
+                                  cudaStream_t stream) {
+    const WinGeom q = win_geom(B, H, W, C);
+    auto go = [&](auto tag, int V) {
+        using T = decltype(tag);
+        dim3 grid;
+        const ReduceGeom g = rowloop_geom(T_, q.Pw, C, V, &grid);
+        const T* xs = static_cast<const T*>(x);
+        const T* ds = static_cast<const T*>(dy);
+        const T* ps = static_cast<const T*>(dp);
+        T* os = static_cast<T*>(dx);
+        if (V == 1)
+            bn_relu_pool_bwd_apply_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, ds, ps, mean, rstd, scale, shift, coef1, coef2, os, g, q, tstride);
+        else if constexpr (std::is_same<T, float>::value)
+            bn_relu_pool_bwd_apply_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, ds, ps, mean, rstd, scale, shift, coef1, coef2, os, g, q, tstride);
+        else
+            bn_relu_pool_bwd_apply_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, ds, ps, mean, rstd, scale, shift, coef1, coef2, os, g, q, tstride);
+    };
+    if (dtype_fp32)
+        go(float(), pick_vec<float>(C, {x, dy, dp, dx}));
+    else
+        go(__nv_bfloat16(), pick_vec<__nv_bfloat16>(C, {x, dy, dp, dx}));
     B200_CUDA_CHECK(cudaGetLastError());
     return B200_OK;
 }

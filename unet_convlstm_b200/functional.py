@@ -115,11 +115,17 @@ def permute_cast(x, perm, dtype, pad_to=None):
 # ------------------------------------------------------------------------------------------------
 class ConvBnRelu(torch.autograd.Function):
     """y = relu(bn(conv3x3([x0 ; x1]) + bias)).  The channel concat of Up (unet.py:98) is virtual:
-    the GEMM K loop reads x0 then x1.  BatchNorm statistics are per timestep (unet.py:179-182)."""
+    the GEMM K loop reads x0 then x1.  BatchNorm statistics are per timestep (unet.py:179-182).
+
+    pool=True returns (y, maxpool2x2(y)) -- an encoder output that feeds a skip connection and the MaxPool2d of the
+    next Down stage (unet.py:81, 179-182 -> 196-202): the normalise/ReLU pass writes the pooled tensor too, and in
+    backward the sum of the skip gradient and the routed pool gradient is formed inside the BatchNorm-backward
+    passes instead of by a max-pool backward kernel (ops.bn_relu_fwd / bn_relu_bwd)."""
 
     @staticmethod
-    def forward(ctx, x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, momentum, cache):
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, momentum, cache, pool=False):
         ctx.counted = _count_use(ctx, cache)
+        ctx.set_materialize_grads(False)   # an unused output (skip or pooled) arrives as None, not as a zero tensor
         x0 = _c(x0)
         x1 = None if x1 is None else _c(x1)
         dt = x0.dtype
@@ -138,27 +144,34 @@ class ConvBnRelu(torch.autograd.Function):
         ws = torch.empty((2, T, N), device=x0.device, dtype=torch.float64) if (training and ops.FUSE_BN_STATS) else None
         fused = ops.conv_fwd(x0, x1, wp, bias.detach() if bias is not None else None, ks, z, bn_ws=ws)
         y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum,
-                                   ws=ws if fused else None)
+                                   ws=ws if fused else None, pool=pool)
         ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
         ctx.tstride = stats[4]
         ctx.training, ctx.cache, ctx.has_bias = training, cache, bias is not None
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dpool=None):
         x0, x1, z, weight, gamma, mean, rstd, scale, shift = ctx.saved_tensors
         single = ctx.cache.note_backward() if ctx.counted else True
         dt = z.dtype
-        dy = _c(dy)
-        if dy.dtype != dt:
-            dy = dy.to(dt)
+
+        def as_act(g):
+            if g is None:
+                return None
+            g = _c(g)
+            return g if g.dtype == dt else g.to(dt)
+
+        dy, dpool = as_act(dy), as_act(dpool)
+        if dy is None and dpool is None:
+            return (None,) * 13
         T, B, H, W, N = z.shape
         C0 = x0.shape[-1]
         C1 = 0 if x1 is None else x1.shape[-1]
         K, ks = weight.shape[1], weight.shape[2]
         # the conv-bias gradient comes out of the BatchNorm sums in closed form (zero in training mode)
         dz, dgamma, dbeta, dbias = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
-                                                   ctx.has_bias)
+                                                   ctx.has_bias, dpool=dpool)
         # weight gradient, batched over all T*B images
         def wgrad():
             dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
@@ -188,7 +201,7 @@ class ConvBnRelu(torch.autograd.Function):
                 bg.keep(dweight)
         if not bg.active and (need0 or need1):
             dx0, dx1 = dgrad()
-        return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
+        return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def _dgrad_pack_padded(weight, dt, Kp):

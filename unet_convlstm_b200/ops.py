@@ -325,9 +325,19 @@ def colsum(x2d_rows: int, x, C: int, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------------
 # BatchNorm + ReLU
 # ------------------------------------------------------------------------------------------------
-def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum, ws=None):
+# BatchNorm apply + ReLU + the 2x2 max-pool of the next Down stage in one pass, forward and backward (encoder outputs
+# with even H and W): B200_FUSE_BN_POOL=0 goes back to the separate kernels (PoolFork).
+FUSE_BN_POOL = os.environ.get("B200_FUSE_BN_POOL", "1") != "0"
+
+
+def bn_pool_ok(z) -> bool:
+    return FUSE_BN_POOL and z.shape[2] % 2 == 0 and z.shape[3] % 2 == 0
+
+
+def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum, ws=None, pool=False):
     """Returns (y, stats) with stats = (mean, rstd, scale, shift, tstride); statistics per (t, c).
-    ws: fp64 [2, T, C] sums already produced by the conv epilogue (conv_fwd(..., bn_ws=ws))."""
+    ws: fp64 [2, T, C] sums already produced by the conv epilogue (conv_fwd(..., bn_ws=ws)).
+    pool: returns ((y, maxpool2x2(y)), stats), both outputs written by one kernel (H and W even)."""
     _chk(z, "z")
     T, B, H, W, C = z.shape
     P = B * H * W
@@ -352,21 +362,37 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
                   _p(running_var), eps, momentum, 0, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     tstride = C if training else 0
     y = torch.empty_like(z)
+    if pool:
+        yp = torch.empty((T, B, H // 2, W // 2, C), device=dev, dtype=z.dtype)
+        _lib.call("b200_bn_relu_apply_pool", _p(z), _p(scale), _p(shift), _p(y), _p(yp), T, B, H, W, C, tstride,
+                  _f32(z), _st(), tag=f"C{C} {H}x{W}", work=(None, (2 * z.numel() + yp.numel()) * z.element_size()))
+        return (y, yp), (mean, rstd, scale, shift, tstride)
     _lib.call("b200_bn_relu_apply", _p(z), _p(scale), _p(shift), _p(y), T, P, C, tstride, 1, _f32(z), _st(),
               tag=f"C{C} {H}x{W}", work=(None, 2 * z.numel() * z.element_size()))
     return y, (mean, rstd, scale, shift, tstride)
 
 
-def bn_relu_bwd(z, dy, stats, training, want_dbias=False):
-    """Returns (dz, dgamma, dbeta, dconv_bias)."""
-    _chk(z, "z"), _chk(dy, "dy")
+def bn_relu_bwd(z, dy, stats, training, want_dbias=False, dpool=None):
+    """Returns (dz, dgamma, dbeta, dconv_bias).  dpool: the gradient of maxpool2x2(y) (bn_relu_fwd(..., pool=True)); the
+    gradient of y is then dy (may be None) + dpool routed to the window maxima, formed inside the two passes."""
+    _chk(z, "z")
     mean, rstd, scale, shift, tstride = stats
     T, B, H, W, C = z.shape
     P = B * H * W
     dev = z.device
     ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
-    _lib.call("b200_bn_relu_bwd_reduce", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), T, P, C, tstride,
-              _f32(z), _p(ws[0]), _p(ws[1]), _st(), tag=f"C{C} {H}x{W}", work=(None, 2 * z.numel() * z.element_size()))
+    esz = z.element_size()
+    if dpool is not None:
+        _chk(dpool, "dpool")
+        if dy is not None:
+            _chk(dy, "dy")
+        nb = (1 if dy is None else 2) * z.numel() + dpool.numel()
+        _lib.call("b200_bn_relu_pool_bwd_reduce", _p(z), _p(dy), _p(dpool), _p(mean), _p(rstd), _p(scale), _p(shift), T, B,
+                  H, W, C, tstride, _f32(z), _p(ws[0]), _p(ws[1]), _st(), tag=f"C{C} {H}x{W}", work=(None, nb * esz))
+    else:
+        _chk(dy, "dy")
+        _lib.call("b200_bn_relu_bwd_reduce", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), T, P, C, tstride,
+                  _f32(z), _p(ws[0]), _p(ws[1]), _st(), tag=f"C{C} {H}x{W}", work=(None, 2 * z.numel() * esz))
     coef = torch.empty((2, T, C), device=dev, dtype=torch.float32)
     dgamma = torch.empty(C, device=dev, dtype=torch.float32)
     dbeta = torch.empty(C, device=dev, dtype=torch.float32)
@@ -374,9 +400,14 @@ def bn_relu_bwd(z, dy, stats, training, want_dbias=False):
     _lib.call("b200_bn_bwd_finalize", _p(ws[0]), _p(ws[1]), T, P, C, int(training), _p(scale), _p(coef[0]),
               _p(coef[1]), _p(dgamma), _p(dbeta), _p(dcb), 0, _st())
     dz = torch.empty_like(z)
+    if dpool is not None:
+        _lib.call("b200_bn_relu_pool_bwd_apply", _p(z), _p(dy), _p(dpool), _p(mean), _p(rstd), _p(scale), _p(shift),
+                  _p(coef[0]), _p(coef[1]), _p(dz), T, B, H, W, C, tstride, _f32(z), _st(), tag=f"C{C} {H}x{W}",
+                  work=(None, (nb + z.numel()) * esz))
+        return dz, dgamma, dbeta, dcb
     _lib.call("b200_bn_relu_bwd_apply", _p(z), _p(dy), _p(mean), _p(rstd), _p(scale), _p(shift), _p(coef[0]),
               _p(coef[1]), _p(dz), T, P, C, tstride, _f32(z), _st(), tag=f"C{C} {H}x{W}",
-              work=(None, 3 * z.numel() * z.element_size()))
+              work=(None, 3 * z.numel() * esz))
     return dz, dgamma, dbeta, dcb
 
 
