@@ -279,6 +279,17 @@ int b200_grad_clip_multi(int n, void* const* grads, const long long* numel, cons
 int b200_adamw_multi(int n, void* const* params, const void* const* grads, void* const* exp_avg,
                      void* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
                      float weight_decay, long long step, const double* sqnorm, float max_norm, void* stream);
+/* AdamW of ONE convolution weight [A][B][taps] fp32 (OIHW: A = Cout, B = Cin; IOHW for ConvTranspose2d) that also emits
+ * the GEMM-operand copies of the UPDATED weight -- SURVEY section 8 f1, "fused AdamW that also emits the packed bf16
+ * weights": same arithmetic as b200_adamw_multi, then up to two destinations in the layouts of b200_pack_weight
+ * (dst NULL = unused; dst_fp32, a_contig, flip, tap_pitch, row_pitch, perm_ch, perm_cht as there).  The results are
+ * bit-identical to b200_adamw_multi followed by b200_pack_weight. */
+int b200_adamw_pack(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int A, int B, int taps,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                    const double* sqnorm, float max_norm, void* dst0, int dst0_fp32, int a_contig0, int flip0,
+                    long long tap_pitch0, long long row_pitch0, int perm_ch0, int perm_cht0, void* dst1, int dst1_fp32,
+                    int a_contig1, int flip1, long long tap_pitch1, long long row_pitch1, int perm_ch1, int perm_cht1,
+                    void* stream);
 
 #ifdef __cplusplus
 }

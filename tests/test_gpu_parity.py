@@ -967,9 +967,61 @@ def test_packed_weights_follow_the_optimizer(which):
         b = torch.stack(fresh(x)[0], dim=1)
     assert torch.equal(a, b), float((a - b).abs().max())
     m.train(), fresh.train()
-    a = torch.stack(m(x)[0], dim=1)
-    b = torch.stack(fresh(x)[0], dim=1)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    a = torch.stack(m(xa)[0], dim=1)
+    b = torch.stack(fresh(xb)[0], dim=1)
     assert torch.equal(a, b), float((a - b).abs().max())
+    # ... and differentiate like it: the data-gradient weight copies ([tap flipped][K][N]) follow the optimizer too
+    (a * dy).sum().backward()
+    (b * dy).sum().backward()
+    assert rel(_np(xa.grad), _np(xb.grad)) < 1e-4, rel(_np(xa.grad), _np(xb.grad))
+    if which == "b200" and optim.ADAMW_PACK:
+        # the update kernel emitted the packed copies itself: no weight was re-packed by these two forward/backward passes
+        assert pkg._lib.CALLS.get("b200_adamw_pack", 0) > 0
+        n0 = pkg._lib.CALLS.get("b200_pack_weight", 0)
+        opt.zero_grad(set_to_none=True)
+        (torch.stack(m(x)[0], dim=1) * dy).sum().backward()
+        opt.step()
+        (torch.stack(m(x)[0], dim=1) * dy).sum().backward()
+        assert pkg._lib.CALLS.get("b200_pack_weight", 0) == n0
+
+
+@pytest.mark.parametrize("A,B,taps", [(64, 48, 9), (40, 18, 9), (256, 32, 4), (33, 70, 1)])
+def test_adamw_pack_kernel_matches_update_then_pack(A, B, taps):
+    """b200_adamw_pack = b200_adamw_multi followed by b200_pack_weight, bit for bit: parameter, both moments and two
+    packed destinations (forward layout in bf16, transposed + tap-flipped data-gradient layout in fp32; gate-interleaved
+    rows when A = 4 * Ch), with the clip coefficient read from the device."""
+    import unet_convlstm_b200 as pkg
+    from unet_convlstm_b200 import ops, optim
+    g = torch.Generator(device="cuda").manual_seed(A * B)
+    w = torch.randn(A, B, taps, device="cuda", generator=g)
+    gr = torch.randn(A, B, taps, device="cuda", generator=g)
+    m = 0.1 * torch.randn(A, B, taps, device="cuda", generator=g)
+    v = torch.rand(A, B, taps, device="cuda", generator=g)
+    hyper = (1e-2, 0.9, 0.999, 1e-8, 1e-2)
+    sq = optim.grad_sqnorm([gr])
+    perm = (A // 4, 16) if (A % 64 == 0) else (0, 0)
+    # reference: the multi-tensor update, then the two pack launches
+    w0, m0, v0 = w.clone(), m.clone(), v.clone()
+    pkg._lib.call("b200_adamw_multi", 1, optim._ptr_array([w0]), optim._ptr_array([gr]), optim._ptr_array([m0]),
+                  optim._ptr_array([v0]), optim._numel_array([w0]), *hyper, 3, sq, 1.0, ops._st())
+    f0 = torch.empty(taps, A, B, device="cuda", dtype=torch.bfloat16)
+    d0 = torch.zeros(taps, B + 5, A, device="cuda", dtype=torch.float32)
+    ops._pack(w0, A, B, taps, f0, False, False, A * B, B, *perm)
+    ops._pack(w0, A, B, taps, d0, True, True, (B + 5) * A, A)
+    # fused
+    w1, m1, v1 = w.clone(), m.clone(), v.clone()
+    f1, d1 = torch.empty_like(f0), torch.zeros_like(d0)
+    pkg._lib.call("b200_adamw_pack", w1, gr, m1, v1, A, B, taps, *hyper, 3, sq, 1.0,
+                  f1, 0, 0, 0, A * B, B, *perm, d1, 1, 1, 1, (B + 5) * A, A, 0, 0, ops._st())
+    for a, b in ((w1, w0), (m1, m0), (v1, v0), (f1, f0), (d1, d0)):
+        assert torch.equal(a, b)
+    assert not torch.equal(w1, w)
+    # one destination only
+    w2, m2, v2, f2 = w.clone(), m.clone(), v.clone(), torch.empty_like(f0)
+    pkg._lib.call("b200_adamw_pack", w2, gr, m2, v2, A, B, taps, *hyper, 3, sq, 1.0,
+                  f2, 0, 0, 0, A * B, B, *perm, None, 0, 0, 0, 0, 1, 0, 0, ops._st())
+    assert torch.equal(w2, w0) and torch.equal(f2, f0)
 
 
 @pytest.mark.parametrize("N,K,ks,kpad", [(64, 64, 3, None), (40, 18, 3, 32), (128, 2, 3, 16), (96, 200, 1, None),

@@ -305,6 +305,48 @@ def test_weight_cache_invalidation_rules():
     assert c.note_backward() is True                      # and alone again
 
 
+def test_pack_refresh_plan_and_commit():
+    """functional.pack_refresh_plan / pack_refresh_commit (host logic behind optim.AdamW's b200_adamw_pack route): an
+    entry is offered to the optimizer only while it is valid and only if every recipe derives from the parameters being
+    updated; after the commit it survives the optimizer's own generation bump, and nothing else."""
+    import torch
+    from unet_convlstm_b200 import functional as Fn, ops
+    w, b, other = (torch.nn.Parameter(torch.zeros(4)) for _ in range(3))
+    c, built, redone = Fn.WeightCache(), [], []
+
+    def builder():
+        built.append(1)
+        ops._PACK_RECORDER.append(("pack", w, (2, 2, 1, "out", 0, 0, 0, 4, 2, 0, 0)))
+        ops._PACK_RECORDER.append(("redo", (b,), lambda: redone.append(1)))
+        return len(built)
+
+    get = lambda: c.get("lstm", (w, b), builder)
+    assert get() == 1 and ops._PACK_RECORDER is None
+    upd = {p.data_ptr(): p for p in (w, b, other)}
+    packs, redo, entries = Fn.pack_refresh_plan(upd)
+    assert list(packs) == [w.data_ptr()] and packs[w.data_ptr()][0][3] == "out" and len(redo) == 1 and len(entries) == 1
+    # an optimizer that does not update the bias cannot keep this entry fresh
+    assert Fn.pack_refresh_plan({w.data_ptr(): w}) == ({}, [], [])
+    # the "update": versions move, the closures run, the entry is re-stamped, the post-step hook bumps the generation
+    with torch.no_grad():
+        w.add_(1.0), b.add_(1.0)
+    for fn in redo:
+        fn()
+    Fn.pack_refresh_commit(entries)
+    Fn._bump_generation()
+    assert get() == 1 and redone == [1]                    # still cached: no rebuild after the optimizer step
+    Fn._bump_generation()                                  # somebody else's optimizer stepped
+    assert get() == 2
+    with torch.no_grad():
+        w.add_(1.0)                                        # stale entry (version moved): not offered
+    assert Fn.pack_refresh_plan(upd) == ({}, [], [])
+    assert get() == 3
+    # entries without recipes (e.g. the folded-BatchNorm coefficients) are never offered
+    c2 = Fn.WeightCache()
+    c2.get("bn_eval", (other,), lambda: 0)
+    assert all(e[1] != 0 for e in Fn.pack_refresh_plan(upd)[2])
+
+
 def test_background_stream_guards_on_leaf_state():
     """ops._leaf_takes_gradient_as_is: the background path is only safe when autograd merely stores the gradient."""
     import torch

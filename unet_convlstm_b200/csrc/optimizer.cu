@@ -6,6 +6,7 @@
 // HBM-bound: 4 B/param for the norm, 16 B read + 12 B written per param for the update.
 #include "../../include/b200_convlstm.h"
 #include "common.cuh"
+#include "pack.cuh"
 
 namespace b200 {
 
@@ -135,6 +136,48 @@ __global__ void __launch_bounds__(256) grad_scale_multi_kernel(const __grid_cons
     for (int i = threadIdx.x; i < len; i += 256) g[i] *= clip;
 }
 
+// AdamW of ONE convolution weight [A][B][taps] that also EMITS the GEMM-operand copies of the weight it has just
+// updated ("fused AdamW that also emits the packed bf16 weights"): a block owns a 32 x 32 x taps
+// tile -- 32 runs of 32 * taps contiguous floats of param / grad / exp_avg / exp_avg_sq -- updates it with the
+// arithmetic of adamw_multi_kernel, keeps the new values in shared memory and stores them in up to two packed
+// layouts (pack.cuh; the same stores as pack_weight_kernel).  Replaces one share of the multi-tensor update plus two
+// or three pack launches per weight and step, and the 4 B/param those re-read.
+struct PackDst {
+    void* dst;      // nullptr: unused
+    int fp32;
+    PackGeom g;
+};
+
+__global__ void __launch_bounds__(256) adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, int A, int B, int taps, const AdamCfg c,
+                                                         const double* __restrict__ sqnorm, const PackDst d0, const PackDst d1) {
+    __shared__ float tile[PK_T][PK_PITCH];
+    const int a0 = blockIdx.y * PK_T, b0 = blockIdx.x * PK_T;
+    const int na = min(PK_T, A - a0), nb = min(PK_T, B - b0);
+    const int run = nb * taps;
+    const float clip = clip_coef(sqnorm, c.max_norm);
+    for (int ta = threadIdx.x >> 5; ta < na; ta += 8) {
+        const long long off = (static_cast<long long>(a0 + ta) * B + b0) * taps;
+#pragma unroll 3
+        for (int i = threadIdx.x & 31; i < run; i += 32) {
+            float pp = p[off + i], mm = m[off + i], vv = v[off + i];
+            adamw_one(pp, __ldg(g + off + i), mm, vv, c, clip);
+            p[off + i] = pp, m[off + i] = mm, v[off + i] = vv;
+            tile[ta][i] = pp;
+        }
+    }
+    __syncthreads();
+    const PackDst* ds[2] = {&d0, &d1};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (!ds[k]->dst) continue;
+        if (ds[k]->fp32)
+            pack_store_tile<float>(tile, static_cast<float*>(ds[k]->dst), ds[k]->g, a0, b0, na, nb);
+        else
+            pack_store_tile<__nv_bfloat16>(tile, static_cast<__nv_bfloat16*>(ds[k]->dst), ds[k]->g, a0, b0, na, nb);
+    }
+}
+
 // Calls launch(table) for consecutive groups of <= MT_MAX non-empty tensors.
 template <class F>
 static int for_each_group(int n, float* const* p, float* const* g, float* const* m, float* const* v, const long long* numel,
@@ -228,4 +271,39 @@ extern "C" int b200_adamw_multi(int n, void* const* params, const void* const* g
                               B200_CUDA_CHECK(cudaGetLastError());
                               return B200_OK;
                           });
+}
+
+static bool pack_dst_ok(const void* dst, int A, int taps, long long tap_pitch, long long row_pitch, int perm_ch, int perm_cht) {
+    if (!dst) return true;
+    (void)taps;
+    return tap_pitch >= 0 && row_pitch > 0 && (perm_ch == 0 || (perm_cht > 0 && perm_ch % perm_cht == 0 && A == 4 * perm_ch));
+}
+
+extern "C" int b200_adamw_pack(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int A, int B, int taps,
+                               float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                               const double* sqnorm, float max_norm, void* dst0, int dst0_fp32, int a_contig0, int flip0,
+                               long long tap_pitch0, long long row_pitch0, int perm_ch0, int perm_cht0, void* dst1,
+                               int dst1_fp32, int a_contig1, int flip1, long long tap_pitch1, long long row_pitch1,
+                               int perm_ch1, int perm_cht1, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || A <= 0 || B <= 0 || taps <= 0 || taps > PK_MAX_TAPS || step < 1 ||
+        !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) ||
+        !pack_dst_ok(dst0, A, taps, tap_pitch0, row_pitch0, perm_ch0, perm_cht0) ||
+        !pack_dst_ok(dst1, A, taps, tap_pitch1, row_pitch1, perm_ch1, perm_cht1)) {
+        set_last_error("b200_adamw_pack: bad arguments (taps <= %d; the gate interleave needs A = 4*Ch, Ch %% cht = 0)", PK_MAX_TAPS);
+        return B200_ERR_ARG;
+    }
+    dim3 grid((B + PK_T - 1) / PK_T, (A + PK_T - 1) / PK_T);
+    if (grid.y > 65535) {
+        set_last_error("b200_adamw_pack: A too large");
+        return B200_ERR_SHAPE;
+    }
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+    AdamCfg c{lr, beta1, beta2, eps, weight_decay, static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), max_norm};
+    PackDst d0{dst0, dst0_fp32, PackGeom{A, B, taps, a_contig0 != 0, flip0 != 0, tap_pitch0, row_pitch0, perm_ch0, perm_cht0}};
+    PackDst d1{dst1, dst1_fp32, PackGeom{A, B, taps, a_contig1 != 0, flip1 != 0, tap_pitch1, row_pitch1, perm_ch1, perm_cht1}};
+    adamw_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, A, B, taps, c,
+                                                                            sqnorm, d0, d1);
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
 }

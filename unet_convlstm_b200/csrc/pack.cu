@@ -6,36 +6,9 @@
 // [32 * taps] float runs, coalesced writes of 32 consecutive columns per (tap, row).
 // HBM-bound: 4 B read + 2 B written per parameter (pack), 4 + 4 (unpack).
 #include "../../include/b200_convlstm.h"
-#include "common.cuh"
+#include "pack.cuh"
 
 namespace b200 {
-
-constexpr int PK_T = 32;        // tile edge over both index dimensions
-constexpr int PK_MAX_TAPS = 9;
-constexpr int PK_PITCH = PK_T * PK_MAX_TAPS + 1;  // +1: column reads of the tile are conflict-free
-
-struct PackGeom {
-    int A, B, taps;             // src [A][B][taps] fp32 contiguous (pack) / dst of the same shape (unpack)
-    int a_contig;               // 0: packed[tap'][pa(a)][b]   1: packed[tap'][b][pa(a)]
-    int flip;                   // tap' = taps-1-tap (data-gradient weights) instead of tap
-    long long tap_pitch;        // elements between consecutive tap' planes of the packed tensor
-    long long row_pitch;        // elements between consecutive rows of the packed tensor
-    int perm_ch, perm_cht;      // gate interleave of a (ConvLSTM rows): a = g*Ch + nt*cht + j -> (nt*4 + g)*cht + j; 0 = none
-};
-
-__device__ __forceinline__ int perm_a(int a, const PackGeom& g) {
-    if (g.perm_ch == 0) return a;
-    const int gate = a / g.perm_ch, r = a - gate * g.perm_ch;
-    const int nt = r / g.perm_cht, j = r - nt * g.perm_cht;
-    return (nt * 4 + gate) * g.perm_cht + j;
-}
-
-template <typename TOut>
-__device__ __forceinline__ TOut to_out(float v);
-template <>
-__device__ __forceinline__ float to_out<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
 // grid (ceil(B/32), ceil(A/32)), 256 threads
 template <typename TOut>
@@ -49,28 +22,7 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
         for (int i = threadIdx.x & 31; i < run; i += 32) tile[ta][i] = __ldg(s + i);
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (!g.a_contig) {
-        // one warp per (tap, a) row: 32 consecutive b
-        for (int r = warp; r < g.taps * na; r += 8) {
-            const int tap = r / na, ta = r - tap * na;
-            if (lane < nb) {
-                const int tp = g.flip ? g.taps - 1 - tap : tap;
-                dst[tp * g.tap_pitch + static_cast<long long>(perm_a(a0 + ta, g)) * g.row_pitch + b0 + lane] =
-                    to_out<TOut>(tile[ta][lane * g.taps + tap]);
-            }
-        }
-    } else {
-        // one warp per (tap, b) row: 32 consecutive a (the gate interleave keeps runs of perm_cht >= 16 together)
-        for (int r = warp; r < g.taps * nb; r += 8) {
-            const int tap = r / nb, tb = r - tap * nb;
-            if (lane < na) {
-                const int tp = g.flip ? g.taps - 1 - tap : tap;
-                dst[tp * g.tap_pitch + static_cast<long long>(b0 + tb) * g.row_pitch + perm_a(a0 + lane, g)] =
-                    to_out<TOut>(tile[lane][tb * g.taps + tap]);
-            }
-        }
-    }
+    pack_store_tile<TOut>(tile, dst, g, a0, b0, na, nb);
 }
 
 // packed fp32 [taps][A][ldb] (columns koff.. of each row) -> dst fp32 [A][B][taps];  grid (ceil(B/32), ceil(A/32))

@@ -6,6 +6,8 @@ the backward formulas are the hand-derived autograd of the reference modules in 
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -25,6 +27,46 @@ from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_step
 _reg_step_hook(_bump_generation)
 
 
+_CACHES = weakref.WeakSet()   # every WeightCache alive (pack_refresh_plan)
+
+
+def pack_refresh_plan(updated):
+    """For an optimizer about to update the parameters `updated` ({data_ptr: tensor}): the packed copies it can emit
+    itself.  Returns (packs, redo, entries): packs = {data_ptr: [geometry of ops._pack, ...]} for b200_adamw_pack,
+    redo = closures to run after the update (small derived tensors: the gate-interleaved bias), entries = the cache
+    entries all of whose recipes are covered -- pass them to pack_refresh_commit() after the update.  Only entries that
+    are valid right now and derive from nothing but the parameters in `updated` qualify; everything else is left to the
+    version / generation check of WeightCache.get()."""
+    packs, redo, entries = {}, [], []
+    for cache in list(_CACHES):
+        for ent in cache._d.values():
+            ver, _, recipes, params = ent
+            if not recipes or ver != WeightCache._stamp(params, _OPT_GENERATION[0]):
+                continue
+            ok = all((r[0] == "pack" and _same(updated.get(r[1].data_ptr()), r[1])) or
+                     (r[0] == "redo" and all(_same(updated.get(q.data_ptr()), q) for q in r[1])) for r in recipes)
+            if not ok:
+                continue
+            for r in recipes:
+                if r[0] == "pack":
+                    packs.setdefault(r[1].data_ptr(), []).append(r[2])
+                else:
+                    redo.append(r[2])
+            entries.append(ent)
+    return packs, redo, entries
+
+
+def _same(p, w):
+    return p is not None and p.numel() == w.numel() and p.dtype == w.dtype
+
+
+def pack_refresh_commit(entries):
+    """The packed values of `entries` now hold the updated parameters: stamp them with the parameter versions as they
+    are now and with the optimizer generation the post-step hook (_bump_generation) is about to set."""
+    for ent in entries:
+        ent[0] = WeightCache._stamp(ent[3], _OPT_GENERATION[0] + 1)
+
+
 class WeightCache:
     """Packed (GEMM-layout, activation-dtype) copies of a module's parameters, rebuilt when the parameter changes.
     Two signals: the tensor version (in-place torch ops, load_state_dict, this package's optimizer) and the optimizer
@@ -34,9 +76,10 @@ class WeightCache:
     loop after training keeps its packed weights."""
 
     def __init__(self):
-        self._d = {}
+        self._d = {}          # key -> [version stamp, value, recipes (ops._PACK_RECORDER), params]
         self._open = 0        # forward passes (with a graph) whose backward has not run yet
         self._shared = False  # the parameters were used more than once in the graph(s) still open
+        _CACHES.add(self)
 
     def begin_forward(self, differentiated: bool) -> bool:
         """Call at the top of every forward pass, BEFORE the first get().  Returns `differentiated`."""
@@ -56,13 +99,22 @@ class WeightCache:
             self._shared = False
         return single
 
+    @staticmethod
+    def _stamp(params, generation):
+        return (generation,) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
+
     def get(self, key, params, builder):
-        ver = (_OPT_GENERATION[0],) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        ver = self._stamp(params, _OPT_GENERATION[0])
         hit = self._d.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        val = builder()
-        self._d[key] = (ver, val)
+        recipes = []
+        prev, ops._PACK_RECORDER = ops._PACK_RECORDER, recipes
+        try:
+            val = builder()
+        finally:
+            ops._PACK_RECORDER = prev
+        self._d[key] = [ver, val, recipes, tuple(params)]
         return val
 
     def clear(self):

@@ -125,9 +125,19 @@ def _pack_ok(w: torch.Tensor, taps: int) -> bool:
     return w.dtype == torch.float32 and taps <= 9 and w.is_cuda
 
 
+# While a functional.WeightCache builds an entry, every packed tensor derived from a parameter is noted here with the
+# recipe that produced it -- ("pack", parameter, geometry of b200_pack_weight) or ("redo", parameters, closure) -- so
+# that optim.AdamW can emit the packed copies from its update kernel (b200_adamw_pack) instead of leaving them to be
+# re-packed at their first use in the next forward pass.
+_PACK_RECORDER = None
+
+
 def _pack(w, A, B, taps, out, a_contig, flip, tap_pitch, row_pitch, perm_ch=0, perm_cht=0):
     """b200_pack_weight: tiled layout change [A][B][taps] fp32 -> GEMM operand (see include/b200_convlstm.h)."""
     src = w.detach()
+    if _PACK_RECORDER is not None and src.is_contiguous():
+        _PACK_RECORDER.append(("pack", w, (A, B, taps, out, _f32(out), int(a_contig), int(flip), tap_pitch, row_pitch,
+                                           perm_ch, perm_cht)))
     src = src if src.is_contiguous() else src.contiguous()
     _lib.call("b200_pack_weight", _p(src), A, B, taps, _p(out), _f32(out), int(a_contig), int(flip), tap_pitch,
               row_pitch, perm_ch, perm_cht, _st())
@@ -179,7 +189,13 @@ def pack_lstm_weight(w: torch.Tensor, b: torch.Tensor | None, dtype: torch.dtype
     bp = None
     if b is not None:
         bp = torch.empty(N, device=w.device, dtype=torch.float32)
-        copy_(bp.view(nt, 4, cht), b.detach().reshape(4, nt, cht).permute(1, 0, 2))
+
+        def pack_bias():
+            copy_(bp.view(nt, 4, cht), b.detach().reshape(4, nt, cht).permute(1, 0, 2))
+
+        pack_bias()
+        if _PACK_RECORDER is not None:
+            _PACK_RECORDER.append(("redo", (b,), pack_bias))
     return out, bp
 
 

@@ -12,11 +12,18 @@ device.  fp32 CUDA tensors only; there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
 from . import _lib
+from . import functional as Fn
 from .ops import _p, _st, bump_version
+
+# AdamW.step() emits the packed GEMM-operand copies of the convolution weights from its update kernel (b200_adamw_pack)
+# for every packed copy a functional.WeightCache currently holds; B200_ADAMW_PACK=0: the weights are re-packed at their
+# first use in the next forward pass instead (b200_pack_weight).
+ADAMW_PACK = os.environ.get("B200_ADAMW_PACK", "1") != "0"
 
 
 def _ptr_array(tensors):
@@ -110,6 +117,9 @@ class AdamW(torch.optim.Optimizer):
             groups.append((group, ps, gs))
         if not groups:
             return loss
+        packs, redo, entries = ({}, [], [])
+        if ADAMW_PACK:
+            packs, redo, entries = Fn.pack_refresh_plan({p.data_ptr(): p for _, ps, _ in groups for p in ps})
         sq = None
         if clip_max_norm is not None:
             allg = [g for _, _, gs in groups for g in gs]
@@ -124,11 +134,39 @@ class AdamW(torch.optim.Optimizer):
                 st["step"] += 1
                 by_step.setdefault(int(st["step"]), []).append((p, g, st["exp_avg"], st["exp_avg_sq"]))
             b1, b2 = group["betas"]
-            for t, items in ((t, c) for t, its in by_step.items() for c in _chunks(its)):
-                P, G, M, V = ([it[k] for it in items] for k in range(4))
-                _check(M, "AdamW.step (exp_avg)"), _check(V, "AdamW.step (exp_avg_sq)")
-                _lib.call("b200_adamw_multi", len(P), _ptr_array(P), _ptr_array(G), _ptr_array(M), _ptr_array(V),
-                          _numel_array(P), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                          float(group["weight_decay"]), t, _p(sq), float(clip_max_norm or 0.0), _st())
-                bump_version(*P, *M, *V)  # written through raw pointers: packed-weight caches key on the version
+            hyper = (float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
+            for t, its in by_step.items():
+                # weights with packed copies in a WeightCache: one launch each that updates AND re-packs
+                rest = []
+                for it in its:
+                    geoms = packs.get(it[0].data_ptr())
+                    if geoms:
+                        _check(it[2:], "AdamW.step (moments)")
+                        self._update_and_pack(it, geoms, hyper, t, sq, clip_max_norm)
+                    else:
+                        rest.append(it)
+                for items in _chunks(rest):
+                    P, G, M, V = ([it[k] for it in items] for k in range(4))
+                    _check(M, "AdamW.step (exp_avg)"), _check(V, "AdamW.step (exp_avg_sq)")
+                    _lib.call("b200_adamw_multi", len(P), _ptr_array(P), _ptr_array(G), _ptr_array(M), _ptr_array(V),
+                              _numel_array(P), *hyper, t, _p(sq), float(clip_max_norm or 0.0), _st())
+                    bump_version(*P, *M, *V)  # written through raw pointers: packed-weight caches key on the version
+        for fn in redo:
+            fn()
+        Fn.pack_refresh_commit(entries)
         return loss
+
+    @staticmethod
+    def _update_and_pack(item, geoms, hyper, t, sq, clip_max_norm):
+        """b200_adamw_pack on one weight: the update plus its first two packed copies; further copies (none in this
+        package's models) through b200_pack_weight."""
+        p, g, m, v = item
+        A, B, taps = geoms[0][:3]
+        none = (None, 0, 0, 0, 0, 1, 0, 0)
+        d0 = geoms[0][3:]
+        d1 = geoms[1][3:] if len(geoms) > 1 else none
+        _lib.call("b200_adamw_pack", _p(p), _p(g), _p(m), _p(v), A, B, taps, *hyper, t, _p(sq), float(clip_max_norm or 0.0),
+                  *d0, *d1, _st())
+        bump_version(p, m, v)
+        for geom in geoms[2:]:
+            _lib.call("b200_pack_weight", _p(p.detach()), *geom[:3], _p(geom[3]), *geom[4:], _st())
