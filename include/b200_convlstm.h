@@ -200,6 +200,22 @@ int b200_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp, c
                                 void* dx, int T, long long B, int H, int W, int C, int tstride, int dtype_fp32,
                                 void* stream);
 
+/* BatchNorm2d + ReLU + the 1x1 OutConv with ONE output channel in one pass (the last DoubleConv feeding `outc`,
+ * unet.py:70-71 -> :104, :202-203): out[t][p] = b + sum_c relu(x*scale+shift)[t][p][c] * w[c], fp32; the activation is
+ * never written.  C / 8 (bf16) or C / 4 (fp32) must be a power of two <= 32.  Backward: the data gradient of the 1x1
+ * convolution is dout[p] * w[c], formed inside the two BatchNorm-backward passes; the reduction pass also yields the
+ * OutConv weight gradient dw[c] = sum_{t,p} dout * y (sum_dw: fp64 workspace [C]; dw fp32 [C], may be NULL).  These
+ * replace b200_bn_relu_apply + b200_outconv_fwd and b200_outconv_bwd + b200_bn_relu_bwd_reduce / _apply. */
+int b200_bn_relu_outconv_fwd(const void* x, const float* scale, const float* shift, const float* w, const float* b,
+                             float* out, int T, long long P, int C, int tstride, int dtype_fp32, void* stream);
+int b200_bn_relu_outconv_bwd_reduce(const void* x, const float* dout, const float* w, const float* mean,
+                                    const float* rstd, const float* scale, const float* shift, int T, long long P, int C,
+                                    int tstride, int dtype_fp32, double* sum_g, double* sum_gx, double* sum_dw, float* dw,
+                                    void* stream);
+int b200_bn_relu_outconv_bwd_apply(const void* x, const float* dout, const float* w, const float* mean, const float* rstd,
+                                   const float* scale, const float* shift, const float* coef1, const float* coef2,
+                                   void* dx, int T, long long P, int C, int tstride, int dtype_fp32, void* stream);
+
 /* ConvLSTM gate math when it is not fused into the GEMM epilogue (unet.py:29-35).  z: fp32 [P][4*Ch]
  * pre-activations in the reference's chunk order i|f|g|o; gates: [P][4][Ch] activated. */
 int b200_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next,

@@ -1200,3 +1200,82 @@ def test_model_fused_pool_matches_pool_fork(mode, size):
         a, b = _np(g1[k]), _np(g0[k])
         scale = max(np.abs(b).max(), 1e-6)
         assert np.abs(a - b).max() <= (1e-4 if mode == "fp32" else 3e-2) * scale, (k, np.abs(a - b).max() / scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm + ReLU + 1x1 OutConv in one pass (the last DoubleConv feeding outc)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 2, 8, 12, 64), (2, 3, 5, 7, 16), (2, 1, 4, 4, 8), (1, 2, 3, 3, 32)])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_relu_outconv_fused_matches_separate_kernels(mode, shape, training):
+    """b200_bn_relu_outconv_fwd / _bwd_reduce / _bwd_apply against b200_bn_relu_apply + b200_outconv_fwd and
+    b200_outconv_bwd + b200_bn_relu_bwd_reduce / _apply.  The fused kernels round the activation and the data gradient
+    of the 1x1 convolution exactly as the separate kernels store them, so only summation orders differ."""
+    from unet_convlstm_b200 import ops
+    T, B, H, W, C = shape
+    dt = ops.act_dtype()
+    if not ops.bn_outconv_ok(C, dt, 1):
+        pytest.skip("channel count not covered by the fused kernels in this mode")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    z = torch.randn(shape, device="cuda", generator=g).to(dt)
+    gamma = (0.5 + torch.rand(C, device="cuda", generator=g))
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    w = torch.randn(1, C, device="cuda", generator=g) / C ** 0.5
+    b = torch.randn(1, device="cuda", generator=g)
+    dout = torch.randn((T, B, H, W, 1), device="cuda", generator=g)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    out1, st1 = ops.bn_relu_fwd(z, gamma, beta, rm, rv, training, 1e-5, 0.1, outconv=(w.reshape(-1), b))
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    y0, st0 = ops.bn_relu_fwd(z, gamma, beta, rm2, rv2, training, 1e-5, 0.1)
+    out0 = ops.outconv_fwd(y0, w, b)
+    assert out1.shape == out0.shape and out1.dtype == torch.float32
+    assert rel(_np(out1), _np(out0)) < 1e-5
+    assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
+
+    dy0, dw0, db0 = ops.outconv_bwd(y0, w, dout)
+    dz0, dg0, dbeta0, dc0 = ops.bn_relu_bwd(z, dy0, st0, training, True)
+    dz1, dg1, dbeta1, dc1, dw1 = ops.bn_relu_bwd(z, dout, st1, training, True, outconv_w=w.reshape(-1))
+    db1 = ops.colsum(dout.numel(), dout, 1)
+    tol = 1e-5 if mode == "fp32" else 6e-3
+    assert rel(_np(dz1), _np(dz0)) < tol, rel(_np(dz1), _np(dz0))
+    assert rel2(_np(dz1), _np(dz0)) < (1e-6 if mode == "fp32" else 1e-3)
+    for a, ref in ((dg1, dg0), (dbeta1, dbeta0), (dc1, dc0), (dw1, dw0.reshape(-1)), (db1, db0)):
+        assert np.abs(_np(a) - _np(ref)).max() <= 1e-5 * max(np.abs(_np(ref)).max(), 1.0)
+
+
+def test_model_fused_outconv_matches_separate(mode):
+    """TemporalUNetDualView with the last DoubleConv + OutConv fused against the separate kernels (ops.FUSE_BN_OUTCONV
+    off): output, every parameter gradient (outc.conv.weight / bias included) and the input gradient."""
+    from train.unet import TemporalUNetDualView
+    from unet_convlstm_b200 import ops
+    import unet_convlstm_b200 as pkg
+    torch.manual_seed(4)
+    m = TemporalUNetDualView(base_ch=16 if mode == "bf16" else 8, use_skip_lstm=False).cuda()
+    x = torch.randn(2, 2, 2, 16, 16, device="cuda")
+    w = torch.randn(2, 2, 1, 16, 16, device="cuda")
+    res = []
+    old = ops.FUSE_BN_OUTCONV
+    try:
+        for fuse in (True, False):
+            ops.FUSE_BN_OUTCONV = fuse
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            m.zero_grad(set_to_none=True)
+            n0 = dict(pkg._lib.CALLS)
+            xi = x.clone().requires_grad_(True)
+            out, _ = m(xi)
+            y = torch.stack(out, 0)
+            (y * w).sum().backward()
+            calls = {k: v - n0.get(k, 0) for k, v in pkg._lib.CALLS.items()}
+            res.append((y.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}, xi.grad.clone(), calls))
+            m.load_state_dict(sd)
+    finally:
+        ops.FUSE_BN_OUTCONV = old
+    (y1, g1, dx1, c1), (y0, g0, dx0, c0) = res
+    assert c1.get("b200_bn_relu_outconv_fwd", 0) == 1 and c1.get("b200_outconv_fwd", 0) == 0
+    assert c0.get("b200_bn_relu_outconv_fwd", 0) == 0 and c0.get("b200_outconv_fwd", 0) == 1
+    assert rel(_np(y1), _np(y0)) < 1e-5
+    g1["x"], g0["x"] = dx1, dx0
+    for k in g0:
+        a, b = _np(g1[k]), _np(g0[k])
+        scale = max(np.abs(b).max(), 1e-6)
+        assert np.abs(a - b).max() <= (1e-4 if mode == "fp32" else 3e-2) * scale, (k, np.abs(a - b).max() / scale)

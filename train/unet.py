@@ -122,9 +122,11 @@ class DoubleConv(nn.Module):
             nn.Conv2d(out_ch, out_ch, 3, padding=1), nn.BatchNorm2d(out_ch), nn.ReLU(inplace=True))
         self._caches = (Fn.WeightCache(), Fn.WeightCache())
 
-    def _half(self, i, x0, x1, pool=False):
+    def _half(self, i, x0, x1, pool=False, outc=None):
         """One conv + BatchNorm + ReLU.  pool: returns (y, maxpool2x2(y)) -- the skip tensor and the input of the next
-        Down stage -- from one normalise pass when the fused kernels apply, from a separate max-pool otherwise."""
+        Down stage -- from one normalise pass when the fused kernels apply, from a separate max-pool otherwise.
+        outc (the nn.Conv2d of OutConv): returns outc(y) as fp32 [T,B,H,W,out] -- from the normalise pass itself when
+        there is one output channel (y is then never written), from the separate 1x1 kernels otherwise."""
         conv, bn = self.net[3 * i], self.net[3 * i + 1]
         T = x0.shape[0]
         training = self.training or not bn.track_running_stats
@@ -141,6 +143,8 @@ class DoubleConv(nn.Module):
                                                 bn.eps, conv.bias))
             y = ops.conv_affine_relu(Fn._c(x0), None if x1 is None else Fn._c(x1), wp, scale, shift,
                                      conv.kernel_size[0])
+            if outc is not None:
+                return Fn.OutConv1x1.apply(y, outc.weight, outc.bias)
             return Fn.PoolFork.apply(y) if pool else y
         # momentum=None is torch's cumulative moving average (factor 1 / num_batches_tracked): encoded for the finalize
         # kernel as -(n0 + 1), n0 = the count before this call (one BatchNorm call per timestep, so step t uses n0 + t + 1)
@@ -149,14 +153,18 @@ class DoubleConv(nn.Module):
         else:
             momentum = -(float(bn.num_batches_tracked) + 1.0) if bn.track_running_stats else 0.0
         fuse_pool = pool and ops.bn_pool_ok(x0)
+        fuse_out = outc is not None and ops.bn_outconv_ok(conv.out_channels, x0.dtype, outc.out_channels)
         y = Fn.ConvBnRelu.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                training, bn.eps, momentum, self._caches[i], fuse_pool)
+                                training, bn.eps, momentum, self._caches[i], fuse_pool,
+                                outc.weight if fuse_out else None, outc.bias if fuse_out else None)
         if training and bn.track_running_stats:
             bn.num_batches_tracked += T  # one BatchNorm call per timestep in the reference
+        if outc is not None and not fuse_out:
+            return Fn.OutConv1x1.apply(y, outc.weight, outc.bias)
         return Fn.PoolFork.apply(y) if (pool and not fuse_pool) else y
 
-    def _seq(self, x0, x1=None, pool=False):
-        return self._half(1, self._half(0, x0, x1), None, pool)
+    def _seq(self, x0, x1=None, pool=False, outc=None):
+        return self._half(1, self._half(0, x0, x1), None, pool, outc)
 
     def forward(self, x):
         _require_cuda(x, "DoubleConv")
@@ -187,9 +195,9 @@ class Up(nn.Module):
         self.conv = DoubleConv(in_ch, out_ch)
         self._cache = Fn.WeightCache()
 
-    def _seq(self, x1, x2):
+    def _seq(self, x1, x2, outc=None):
         u = Fn.ConvT2x2.apply(x1, self.up.weight, self.up.bias, x2.shape[2], x2.shape[3], self._cache)
-        return self.conv._seq(x2, u)  # cat([skip, upsampled]) is virtual: two sources of one K loop
+        return self.conv._seq(x2, u, False, outc)  # cat([skip, upsampled]) is virtual: two sources of one K loop
 
     def forward(self, x1, x2):
         _require_cuda(x1, "Up")
@@ -292,8 +300,9 @@ class TemporalUNetDualView(nn.Module):
         d3 = self.up3._seq(hb, x3)
         d2 = self.up2._seq(d3, x2)
         d1 = self.up1._seq(d2, x1)
-        d0 = self.up0._seq(d1, x0)
-        y = self.outc._seq(d0)  # fp32 [T,B,H,W,out]
+        # the last DoubleConv and the 1x1 output convolution: fp32 [T,B,H,W,out]; with one output channel the normalise
+        # pass of the DoubleConv produces it directly (the 64-channel full-resolution activation is never written)
+        y = self.up0._seq(d1, x0, self.outc.conv)
 
         # list of T frames as views of one buffer.  unbind, not T x select: the backward of unbind stacks the T frame
         # gradients in one pass; T selects each materialise a full-size zero tensor that autograd then adds up

@@ -513,6 +513,34 @@ extern "C" int b200_bn_relu_pool_bwd_apply(const void* x, const void* dy, const 
                                          dtype_fp32, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int b200_bn_relu_outconv_fwd(const void* x, const float* scale, const float* shift, const float* w,
+                                        const float* b, float* out, int T, long long P, int C, int tstride,
+                                        int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && scale && shift && w && out && T > 0 && P > 0 && C > 0, "b200_bn_relu_outconv_fwd");
+    return launch_bn_relu_outconv_fwd(x, scale, shift, w, b, out, T, P, C, tstride, dtype_fp32,
+                                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_outconv_bwd_reduce(const void* x, const float* dout, const float* w, const float* mean,
+                                               const float* rstd, const float* scale, const float* shift, int T,
+                                               long long P, int C, int tstride, int dtype_fp32, double* sum_g,
+                                               double* sum_gx, double* sum_dw, float* dw, void* stream) {
+    B200_REQUIRE(x && dout && w && mean && rstd && scale && shift && sum_g && sum_gx && sum_dw && T > 0 && P > 0 && C > 0,
+                 "b200_bn_relu_outconv_bwd_reduce");
+    return launch_bn_relu_outconv_bwd_reduce(x, dout, w, mean, rstd, scale, shift, T, P, C, tstride, dtype_fp32, sum_g,
+                                             sum_gx, sum_dw, dw, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_relu_outconv_bwd_apply(const void* x, const float* dout, const float* w, const float* mean,
+                                              const float* rstd, const float* scale, const float* shift,
+                                              const float* coef1, const float* coef2, void* dx, int T, long long P,
+                                              int C, int tstride, int dtype_fp32, void* stream) {
+    B200_REQUIRE(x && dout && w && mean && rstd && scale && shift && coef1 && coef2 && dx && T > 0 && P > 0 && C > 0,
+                 "b200_bn_relu_outconv_bwd_apply");
+    return launch_bn_relu_outconv_bwd_apply(x, dout, w, mean, rstd, scale, shift, coef1, coef2, dx, T, P, C, tstride,
+                                            dtype_fp32, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next,
                                    long long P, int Ch, int dtype_fp32, void* stream) {
     B200_REQUIRE(z && gates && c_next && h_next && P > 0 && Ch > 0, "b200_lstm_gates_fwd");

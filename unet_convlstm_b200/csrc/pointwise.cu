@@ -1151,6 +1151,328 @@ int launch_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp,
 }
 
 // ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU + the 1x1 output convolution in one pass (the last DoubleConv feeds OutConv with out_channels = 1,
+// unet.py:70-71 -> :104, :202-203).  Forward: out[p] = b + sum_c relu(x*scale+shift)[p][c] * w[c]; the 64-channel
+// full-resolution activation is NEVER written.  Backward: the data gradient of the 1x1 convolution is the rank-1
+// product dout[p] * w[c], so the BatchNorm-backward passes form it on the fly instead of reading a stored tensor, and
+// the weight gradient dw[c] = sum_p dout[p] * y[p][c] rides along in the reduction pass with y recomputed.  Separately
+// that is apply (r + w) + outconv (r) forward and outconv wgrad (r) + dgrad (w) + BatchNorm sums (2r) + apply (2r + w)
+// backward = 10 passes over the largest activation tensor of the network; fused it is 1 + 1 + 2.  Roundings follow the
+// separate kernels (y and the data gradient as they would have been STORED in T), the summation orders differ.
+// A pixel's C / V channel vectors sit in C / V consecutive lanes (a power of two <= 32).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_relu_outconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, const float* __restrict__ w,
+                                                                  const float* __restrict__ b, float* __restrict__ out,
+                                                                  const ReduceGeom g, int tstride) {
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;       // g.cvb == C / V divides 32: the lanes of one pixel are one aligned shuffle group
+    const int cv = tid - r * g.cvb;
+    const int c = cv * V;
+    const int t = blockIdx.z;
+    float sc[V], sh[V], wv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = __ldg(scale + t * tstride + c + j);
+        sh[j] = __ldg(shift + t * tstride + c + j);
+        wv[j] = __ldg(w + c + j);
+    }
+    const float bias = b ? __ldg(b) : 0.f;
+    const long long p_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long p_end = p_begin + g.rows_per_block;
+    if (p_end > g.P) p_end = g.P;
+    const long long base = static_cast<long long>(t) * g.P;
+    constexpr int U = 4;
+    const long long step = g.rows_per_iter;
+    // block-uniform trip count: every lane takes part in the shuffles
+    for (long long p0 = p_begin; p0 < p_end; p0 += U * step) {
+        RawVec<T, V> rx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + u * step + r;
+            if (p < p_end) ld_raw<T, V>(x + (base + p) * g.C + c, rx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + u * step + r;
+            float acc = 0.f;
+            if (p < p_end) {
+                float f[V];
+                unpack_raw<T, V>(rx[u], f);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc = fmaf(as_stored<T>(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f)), wv[j], acc);
+            }
+            for (int s = g.cvb >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            if (p < p_end && cv == 0) out[base + p] = acc + bias;
+        }
+    }
+}
+
+static bool outconv_fusable(int C, int V) {
+    const int cv = C / V;
+    return C % V == 0 && cv >= 1 && cv <= 32 && (cv & (cv - 1)) == 0;
+}
+
+// rows per block for the pixel-group kernels: cvb = C / V exactly (no idle threads), grid ~16 blocks per SM
+static ReduceGeom pixgroup_geom(int T_, long long P, int C, int V, dim3* grid) {
+    ReduceGeom g;
+    g.T = T_;
+    g.P = P;
+    g.C = C;
+    g.cvb = C / V;
+    g.rows_per_iter = 256 / g.cvb;
+    long long want_x = (16LL * num_sms() + T_ - 1) / T_;
+    long long max_x = (P + 8LL * g.rows_per_iter - 1) / (8LL * g.rows_per_iter);
+    if (want_x > max_x) want_x = max_x;
+    if (want_x < 1) want_x = 1;
+    g.rows_per_block = (P + want_x - 1) / want_x;
+    *grid = dim3(static_cast<unsigned>((P + g.rows_per_block - 1) / g.rows_per_block), 1, T_);
+    return g;
+}
+
+int launch_bn_relu_outconv_fwd(const void* x, const float* scale, const float* shift, const float* w, const float* b,
+                               float* out, int T_, long long P, int C, int tstride, int dtype_fp32, cudaStream_t stream) {
+    auto go = [&](auto tag, int V) -> int {
+        using T = decltype(tag);
+        if (!outconv_fusable(C, V)) {
+            set_last_error("b200_bn_relu_outconv_fwd: C / %d must be a power of two <= 32 (C = %d)", V, C);
+            return B200_ERR_SHAPE;
+        }
+        dim3 grid;
+        const ReduceGeom g = pixgroup_geom(T_, P, C, V, &grid);
+        const T* xs = static_cast<const T*>(x);
+        if (V == 1)
+            bn_relu_outconv_fwd_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, scale, shift, w, b, out, g, tstride);
+        else if constexpr (std::is_same<T, float>::value)
+            bn_relu_outconv_fwd_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, scale, shift, w, b, out, g, tstride);
+        else
+            bn_relu_outconv_fwd_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, scale, shift, w, b, out, g, tstride);
+        return B200_OK;
+    };
+    const int rc = dtype_fp32 ? go(float(), pick_vec<float>(C, {x})) : go(__nv_bfloat16(), pick_vec<__nv_bfloat16>(C, {x}));
+    if (rc != B200_OK) return rc;
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+// sum_g[t][c] = sum_p g, sum_gx[t][c] = sum_p g * xhat (as BnBwdReduceOp) with g = stored(dout[p] * w[c]) * [relu active],
+// and dw[c] += sum_p dout[p] * stored(y[p][c]) over ALL t.  Same block / thread layout as colreduce_kernel.
+template <typename T, int V, typename Acc>
+__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : 3))
+bn_relu_outconv_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ dout, const float* __restrict__ w,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, const ReduceGeom g,
+                                  int tstride, double* __restrict__ sum_g, double* __restrict__ sum_gx,
+                                  double* __restrict__ sum_dw) {
+    constexpr int HV = V > 4 ? 4 : V;
+    __shared__ Acc red[3][256 * HV];
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;
+    const int cv = tid - r * g.cvb;
+    const int c = cv * V;
+    const int t = blockIdx.z;
+    const long long p_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long p_end = p_begin + g.rows_per_block;
+    if (p_end > g.P) p_end = g.P;
+    const long long base = static_cast<long long>(t) * g.P;
+    float sc[V], sh[V], wv[V];
+    Acc a0[V], a1[V], a2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        sc[j] = __ldg(scale + t * tstride + c + j);
+        sh[j] = __ldg(shift + t * tstride + c + j);
+        wv[j] = __ldg(w + c + j);
+        a0[j] = a1[j] = a2[j] = Acc(0);
+    }
+    auto accum = [&](const RawVec<T, V>& rx, float d) {
+        float fx[V];
+        unpack_raw<T, V>(rx, fx);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float yv = fmaf(fx[j], sc[j], sh[j]);
+            const float gq = yv > 0.f ? as_stored<T>(d * wv[j]) : 0.f;
+            a0[j] += Acc(gq);
+            a1[j] += Acc(gq) * Acc(fx[j]);
+            a2[j] += Acc(d) * Acc(as_stored<T>(fmaxf(yv, 0.f)));
+        }
+    };
+    constexpr int U = 4;
+    const long long step = g.rows_per_iter;
+    long long p = p_begin + r;
+    for (; p + (U - 1) * step < p_end; p += U * step) {
+        RawVec<T, V> rx[U];
+        float d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ld_raw<T, V>(x + (base + p + u * step) * g.C + c, rx[u]);
+            d[u] = __ldg(dout + base + p + u * step);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) accum(rx[u], d[u]);
+    }
+    for (; p < p_end; p += step) {
+        RawVec<T, V> rx;
+        ld_raw<T, V>(x + (base + p) * g.C + c, rx);
+        accum(rx, __ldg(dout + base + p));
+    }
+#pragma unroll
+    for (int half = 0; half < V / HV; ++half) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < HV; ++j) {
+            red[0][tid * HV + j] = a0[half * HV + j];
+            red[1][tid * HV + j] = a1[half * HV + j];
+            red[2][tid * HV + j] = a2[half * HV + j];
+        }
+        __syncthreads();
+        if (r == 0) {
+#pragma unroll
+            for (int j = 0; j < HV; ++j) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                for (int rr = 0; rr < g.rows_per_iter; ++rr) {
+                    s0 += static_cast<double>(red[0][(rr * g.cvb + cv) * HV + j]);
+                    s1 += static_cast<double>(red[1][(rr * g.cvb + cv) * HV + j]);
+                    s2 += static_cast<double>(red[2][(rr * g.cvb + cv) * HV + j]);
+                }
+                const int cc = c + half * HV + j;
+                const int i = t * tstride + cc;
+                s1 = static_cast<double>(__ldg(rstd + i)) * (s1 - static_cast<double>(__ldg(mean + i)) * s0);
+                atomicAdd(sum_g + static_cast<long long>(t) * g.C + cc, s0);
+                atomicAdd(sum_gx + static_cast<long long>(t) * g.C + cc, s1);
+                atomicAdd(sum_dw + cc, s2);
+            }
+        }
+    }
+}
+
+int launch_bn_relu_outconv_bwd_reduce(const void* x, const float* dout, const float* w, const float* mean, const float* rstd,
+                                      const float* scale, const float* shift, int T_, long long P, int C, int tstride,
+                                      int dtype_fp32, double* sum_g, double* sum_gx, double* sum_dw, float* dw,
+                                      cudaStream_t stream) {
+    B200_CUDA_CHECK(cudaMemsetAsync(sum_g, 0, sizeof(double) * T_ * C, stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(sum_gx, 0, sizeof(double) * T_ * C, stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(sum_dw, 0, sizeof(double) * C, stream));
+    auto go = [&](auto tag, int V) -> int {
+        using T = decltype(tag);
+        using Acc = typename std::conditional<std::is_same<T, float>::value, double, float>::type;
+        if (!outconv_fusable(C, V)) {
+            set_last_error("b200_bn_relu_outconv_bwd_reduce: C / %d must be a power of two <= 32 (C = %d)", V, C);
+            return B200_ERR_SHAPE;
+        }
+        ReduceGeom g;
+        g.T = T_; g.P = P; g.C = C;
+        g.cvb = C / V;
+        g.rows_per_iter = 256 / g.cvb;
+        // two full waves at three resident blocks per SM, at least 4 iterations per thread (see launch_colreduce)
+        long long want_x = (6LL * num_sms()) / T_;
+        long long max_x = (P + 4LL * g.rows_per_iter - 1) / (4LL * g.rows_per_iter);
+        if (want_x > max_x) want_x = max_x;
+        if (want_x < 1) want_x = 1;
+        g.rows_per_block = (P + want_x - 1) / want_x;
+        dim3 grid(static_cast<unsigned>((P + g.rows_per_block - 1) / g.rows_per_block), 1, T_);
+        const T* xs = static_cast<const T*>(x);
+        if (V == 1)
+            bn_relu_outconv_bwd_reduce_kernel<T, 1, Acc><<<grid, 256, 0, stream>>>(xs, dout, w, mean, rstd, scale, shift, g, tstride, sum_g, sum_gx, sum_dw);
+        else if constexpr (std::is_same<T, float>::value)
+            bn_relu_outconv_bwd_reduce_kernel<T, 4, Acc><<<grid, 256, 0, stream>>>(xs, dout, w, mean, rstd, scale, shift, g, tstride, sum_g, sum_gx, sum_dw);
+        else
+            bn_relu_outconv_bwd_reduce_kernel<T, 8, Acc><<<grid, 256, 0, stream>>>(xs, dout, w, mean, rstd, scale, shift, g, tstride, sum_g, sum_gx, sum_dw);
+        return B200_OK;
+    };
+    const int rc = dtype_fp32 ? go(float(), pick_vec<float>(C, {x})) : go(__nv_bfloat16(), pick_vec<__nv_bfloat16>(C, {x}));
+    if (rc != B200_OK) return rc;
+    B200_CUDA_CHECK(cudaGetLastError());
+    return dw ? launch_cast_double(sum_dw, dw, C, 0, stream) : B200_OK;
+}
+
+// dx = scale * g + ka * x + kb as bn_relu_bwd_apply_kernel, g = stored(dout[p] * w[c]) where the ReLU is active
+template <typename T, int V>
+__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : 3))
+bn_relu_outconv_bwd_apply_kernel(const T* __restrict__ x, const float* __restrict__ dout, const float* __restrict__ w,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                 const float* __restrict__ coef1, const float* __restrict__ coef2, T* __restrict__ dx,
+                                 const ReduceGeom g, int tstride) {
+    const int tid = threadIdx.x;
+    const int r = tid / g.cvb;
+    const int cv = tid - r * g.cvb;
+    const int c = (blockIdx.y * g.cvb + cv) * V;
+    const int t = blockIdx.z;
+    if (r >= g.rows_per_iter || c >= g.C) return;
+    float sc[V], sh[V], ka[V], kb[V], wv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int ps = t * tstride + c + j, pc = t * g.C + c + j;
+        sc[j] = __ldg(scale + ps);
+        sh[j] = __ldg(shift + ps);
+        wv[j] = __ldg(w + c + j);
+        const float rc2 = __ldg(rstd + ps) * __ldg(coef2 + pc);
+        ka[j] = -sc[j] * rc2;
+        kb[j] = sc[j] * (rc2 * __ldg(mean + ps) - __ldg(coef1 + pc));
+    }
+    const long long p_begin = static_cast<long long>(blockIdx.x) * g.rows_per_block;
+    long long p_end = p_begin + g.rows_per_block;
+    if (p_end > g.P) p_end = g.P;
+    const long long base = static_cast<long long>(t) * g.P;
+    auto apply = [&](const RawVec<T, V>& rx, float d, long long off) {
+        float fx[V], fd[V];
+        unpack_raw<T, V>(rx, fx);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float yv = fmaf(fx[j], sc[j], sh[j]);
+            const float gq = yv > 0.f ? as_stored<T>(d * wv[j]) : 0.f;
+            fd[j] = fmaf(sc[j], gq, fmaf(ka[j], fx[j], kb[j]));
+        }
+        stv<T, V>(dx + off, fd);
+    };
+    constexpr int U = 4;
+    const long long step = g.rows_per_iter;
+    long long p = p_begin + r;
+    for (; p + (U - 1) * step < p_end; p += U * step) {
+        RawVec<T, V> rx[U];
+        float d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ld_raw<T, V>(x + (base + p + u * step) * g.C + c, rx[u]);
+            d[u] = __ldg(dout + base + p + u * step);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) apply(rx[u], d[u], (base + p + u * step) * g.C + c);
+    }
+    for (; p < p_end; p += step) {
+        RawVec<T, V> rx;
+        ld_raw<T, V>(x + (base + p) * g.C + c, rx);
+        apply(rx, __ldg(dout + base + p), (base + p) * g.C + c);
+    }
+}
+
+int launch_bn_relu_outconv_bwd_apply(const void* x, const float* dout, const float* w, const float* mean, const float* rstd,
+                                     const float* scale, const float* shift, const float* coef1, const float* coef2,
+                                     void* dx, int T_, long long P, int C, int tstride, int dtype_fp32,
+                                     cudaStream_t stream) {
+    auto go = [&](auto tag, int V) {
+        using T = decltype(tag);
+        dim3 grid;
+        const ReduceGeom g = rowloop_geom(T_, P, C, V, &grid);
+        const T* xs = static_cast<const T*>(x);
+        T* os = static_cast<T*>(dx);
+        if (V == 1)
+            bn_relu_outconv_bwd_apply_kernel<T, 1><<<grid, 256, 0, stream>>>(xs, dout, w, mean, rstd, scale, shift, coef1, coef2, os, g, tstride);
+        else if constexpr (std::is_same<T, float>::value)
+            bn_relu_outconv_bwd_apply_kernel<T, 4><<<grid, 256, 0, stream>>>(xs, dout, w, mean, rstd, scale, shift, coef1, coef2, os, g, tstride);
+        else
+            bn_relu_outconv_bwd_apply_kernel<T, 8><<<grid, 256, 0, stream>>>(xs, dout, w, mean, rstd, scale, shift, coef1, coef2, os, g, tstride);
+    };
+    if (dtype_fp32)
+        go(float(), pick_vec<float>(C, {x, dx}));
+    else
+        go(__nv_bfloat16(), pick_vec<__nv_bfloat16>(C, {x, dx}));
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // ConvLSTM gate math (ConvLSTMCell.forward, unet.py:29-35) and its BPTT gradient
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>

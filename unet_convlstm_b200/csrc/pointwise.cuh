@@ -38,6 +38,16 @@ int launch_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp,
                                   const float* scale, const float* shift, const float* coef1, const float* coef2,
                                   void* dx, int T, long long B, int H, int W, int C, int tstride, int dtype_fp32,
                                   cudaStream_t stream);
+int launch_bn_relu_outconv_fwd(const void* x, const float* scale, const float* shift, const float* w, const float* b,
+                               float* out, int T, long long P, int C, int tstride, int dtype_fp32, cudaStream_t stream);
+int launch_bn_relu_outconv_bwd_reduce(const void* x, const float* dout, const float* w, const float* mean, const float* rstd,
+                                      const float* scale, const float* shift, int T, long long P, int C, int tstride,
+                                      int dtype_fp32, double* sum_g, double* sum_gx, double* sum_dw, float* dw,
+                                      cudaStream_t stream);
+int launch_bn_relu_outconv_bwd_apply(const void* x, const float* dout, const float* w, const float* mean, const float* rstd,
+                                     const float* scale, const float* shift, const float* coef1, const float* coef2,
+                                     void* dx, int T, long long P, int C, int tstride, int dtype_fp32,
+                                     cudaStream_t stream);
 int launch_lstm_gates_fwd(const float* z, const float* c_prev, void* gates, float* c_next, void* h_next, long long P,
                           int Ch, int dtype_fp32, cudaStream_t stream);
 int launch_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_next, const void* dh_a,

@@ -175,7 +175,10 @@ class ConvBnRelu(torch.autograd.Function):
     passes instead of by a max-pool backward kernel (ops.bn_relu_fwd / bn_relu_bwd)."""
 
     @staticmethod
-    def forward(ctx, x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, momentum, cache, pool=False):
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, momentum, cache, pool=False,
+                out_w=None, out_b=None):
+        """out_w [1, N, 1, 1] / out_b [1] (OutConv, unet.py:101-107, one output channel): returns
+        outconv(relu(bn(conv))) as fp32 [T,B,H,W,1] from the normalise pass; the activation is not materialised."""
         ctx.counted = _count_use(ctx, cache)
         ctx.set_materialize_grads(False)   # an unused output (skip or pooled) arrives as None, not as a zero tensor
         x0 = _c(x0)
@@ -195,16 +198,20 @@ class ConvBnRelu(torch.autograd.Function):
         # b200_bn_stats pass, profiles/r01_fused_bn_stats_measured.txt), so it is opt-in.
         ws = torch.empty((2, T, N), device=x0.device, dtype=torch.float64) if (training and ops.FUSE_BN_STATS) else None
         fused = ops.conv_fwd(x0, x1, wp, bias.detach() if bias is not None else None, ks, z, bn_ws=ws)
+        outconv = None
+        if out_w is not None:
+            outconv = (out_w.detach().reshape(-1), None if out_b is None else out_b.detach())
         y, stats = ops.bn_relu_fwd(z, gamma.detach(), beta.detach(), rm, rv, training, eps, momentum,
-                                   ws=ws if fused else None, pool=pool)
-        ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4])
+                                   ws=ws if fused else None, pool=pool, outconv=outconv)
+        ctx.save_for_backward(x0, x1, z, weight, gamma, *stats[:4], out_w)
         ctx.tstride = stats[4]
         ctx.training, ctx.cache, ctx.has_bias = training, cache, bias is not None
+        ctx.has_out_b = out_b is not None
         return y
 
     @staticmethod
     def backward(ctx, dy, dpool=None):
-        x0, x1, z, weight, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        x0, x1, z, weight, gamma, mean, rstd, scale, shift, out_w = ctx.saved_tensors
         single = ctx.cache.note_backward() if ctx.counted else True
         dt = z.dtype
 
@@ -214,16 +221,29 @@ class ConvBnRelu(torch.autograd.Function):
             g = _c(g)
             return g if g.dtype == dt else g.to(dt)
 
-        dy, dpool = as_act(dy), as_act(dpool)
-        if dy is None and dpool is None:
-            return (None,) * 13
+        d_out_w = d_out_b = None
+        if out_w is not None:
+            if dy is None:
+                return (None,) * 15
+            dy = _c(dy).float()                 # gradient of the 1x1 convolution's output, fp32 [T,B,H,W,1]
+        else:
+            dy, dpool = as_act(dy), as_act(dpool)
+            if dy is None and dpool is None:
+                return (None,) * 15
         T, B, H, W, N = z.shape
         C0 = x0.shape[-1]
         C1 = 0 if x1 is None else x1.shape[-1]
         K, ks = weight.shape[1], weight.shape[2]
         # the conv-bias gradient comes out of the BatchNorm sums in closed form (zero in training mode)
-        dz, dgamma, dbeta, dbias = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
-                                                   ctx.has_bias, dpool=dpool)
+        if out_w is not None:
+            dz, dgamma, dbeta, dbias, dwo = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
+                                                            ctx.has_bias, outconv_w=out_w.detach().reshape(-1))
+            d_out_w = dwo.view_as(out_w)
+            if ctx.has_out_b:
+                d_out_b = ops.colsum(dy.numel(), dy, 1)
+        else:
+            dz, dgamma, dbeta, dbias = ops.bn_relu_bwd(z, dy, (mean, rstd, scale, shift, ctx.tstride), ctx.training,
+                                                       ctx.has_bias, dpool=dpool)
         # weight gradient, batched over all T*B images
         def wgrad():
             dwp = torch.zeros((ks * ks, N, C0 + C1), device=z.device, dtype=torch.float32)
@@ -253,7 +273,7 @@ class ConvBnRelu(torch.autograd.Function):
                 bg.keep(dweight)
         if not bg.active and (need0 or need1):
             dx0, dx1 = dgrad()
-        return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx0, dx1, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None, None, d_out_w, d_out_b
 
 
 def _dgrad_pack_padded(weight, dt, Kp):

@@ -350,10 +350,24 @@ def bn_pool_ok(z) -> bool:
     return FUSE_BN_POOL and z.shape[2] % 2 == 0 and z.shape[3] % 2 == 0
 
 
-def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum, ws=None, pool=False):
+# BatchNorm apply + ReLU + the 1x1 OutConv (one output channel) in one pass, forward and backward: the last DoubleConv's
+# full-resolution activation and its gradient are never materialised.  B200_FUSE_BN_OUTCONV=0: separate kernels.
+FUSE_BN_OUTCONV = os.environ.get("B200_FUSE_BN_OUTCONV", "1") != "0"
+
+
+def bn_outconv_ok(C: int, dtype, out_channels: int) -> bool:
+    """C channels of `dtype` activations into a 1x1 convolution with `out_channels` outputs: can the fused kernels run?"""
+    V = 4 if dtype == torch.float32 else 8
+    cv = C // V
+    return FUSE_BN_OUTCONV and out_channels == 1 and C % V == 0 and 1 <= cv <= 32 and (cv & (cv - 1)) == 0
+
+
+def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, momentum, ws=None, pool=False, outconv=None):
     """Returns (y, stats) with stats = (mean, rstd, scale, shift, tstride); statistics per (t, c).
     ws: fp64 [2, T, C] sums already produced by the conv epilogue (conv_fwd(..., bn_ws=ws)).
-    pool: returns ((y, maxpool2x2(y)), stats), both outputs written by one kernel (H and W even)."""
+    pool: returns ((y, maxpool2x2(y)), stats), both outputs written by one kernel (H and W even).
+    outconv = (w fp32 [C], b fp32 [1] or None): returns (out fp32 [T,B,H,W,1], stats) with out = outconv1x1(y); y itself
+    is not written (bn_outconv_ok)."""
     _chk(z, "z")
     T, B, H, W, C = z.shape
     P = B * H * W
@@ -377,6 +391,12 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
         _lib.call("b200_bn_finalize", None, None, 1, P, C, _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), eps, momentum, 0, _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     tstride = C if training else 0
+    if outconv is not None:
+        w, b = outconv
+        out = torch.empty((T, B, H, W, 1), device=dev, dtype=torch.float32)
+        _lib.call("b200_bn_relu_outconv_fwd", _p(z), _p(scale), _p(shift), _p(w), _p(b), _p(out), T, P, C, tstride,
+                  _f32(z), _st(), tag=f"C{C} {H}x{W}", work=(None, z.numel() * z.element_size() + out.numel() * 4))
+        return out, (mean, rstd, scale, shift, tstride)
     y = torch.empty_like(z)
     if pool:
         yp = torch.empty((T, B, H // 2, W // 2, C), device=dev, dtype=z.dtype)
@@ -388,9 +408,11 @@ def bn_relu_fwd(z, gamma, beta, running_mean, running_var, training, eps, moment
     return y, (mean, rstd, scale, shift, tstride)
 
 
-def bn_relu_bwd(z, dy, stats, training, want_dbias=False, dpool=None):
+def bn_relu_bwd(z, dy, stats, training, want_dbias=False, dpool=None, outconv_w=None):
     """Returns (dz, dgamma, dbeta, dconv_bias).  dpool: the gradient of maxpool2x2(y) (bn_relu_fwd(..., pool=True)); the
-    gradient of y is then dy (may be None) + dpool routed to the window maxima, formed inside the two passes."""
+    gradient of y is then dy (may be None) + dpool routed to the window maxima, formed inside the two passes.
+    outconv_w (fp32 [C]; bn_relu_fwd(..., outconv=...)): dy is the gradient of the 1x1 convolution's OUTPUT, fp32
+    [T,B,H,W,1]; returns (dz, dgamma, dbeta, dconv_bias, d outconv_w)."""
     _chk(z, "z")
     mean, rstd, scale, shift, tstride = stats
     T, B, H, W, C = z.shape
@@ -398,7 +420,17 @@ def bn_relu_bwd(z, dy, stats, training, want_dbias=False, dpool=None):
     dev = z.device
     ws = torch.empty((2, T, C), device=dev, dtype=torch.float64)
     esz = z.element_size()
-    if dpool is not None:
+    dw_out = None
+    if outconv_w is not None:
+        _chk(dy, "dout")
+        if dy.dtype != torch.float32 or dy.numel() != T * P:
+            raise ValueError("bn_relu_bwd(outconv_w=...): dy must be the fp32 [T,B,H,W,1] gradient of the 1x1 convolution")
+        wsw = torch.empty(C, device=dev, dtype=torch.float64)
+        dw_out = torch.empty(C, device=dev, dtype=torch.float32)
+        _lib.call("b200_bn_relu_outconv_bwd_reduce", _p(z), _p(dy), _p(outconv_w), _p(mean), _p(rstd), _p(scale), _p(shift),
+                  T, P, C, tstride, _f32(z), _p(ws[0]), _p(ws[1]), _p(wsw), _p(dw_out), _st(), tag=f"C{C} {H}x{W}",
+                  work=(None, z.numel() * esz + dy.numel() * 4))
+    elif dpool is not None:
         _chk(dpool, "dpool")
         if dy is not None:
             _chk(dy, "dy")
@@ -416,6 +448,11 @@ def bn_relu_bwd(z, dy, stats, training, want_dbias=False, dpool=None):
     _lib.call("b200_bn_bwd_finalize", _p(ws[0]), _p(ws[1]), T, P, C, int(training), _p(scale), _p(coef[0]),
               _p(coef[1]), _p(dgamma), _p(dbeta), _p(dcb), 0, _st())
     dz = torch.empty_like(z)
+    if outconv_w is not None:
+        _lib.call("b200_bn_relu_outconv_bwd_apply", _p(z), _p(dy), _p(outconv_w), _p(mean), _p(rstd), _p(scale), _p(shift),
+                  _p(coef[0]), _p(coef[1]), _p(dz), T, P, C, tstride, _f32(z), _st(), tag=f"C{C} {H}x{W}",
+                  work=(None, 2 * z.numel() * esz + dy.numel() * 4))
+        return dz, dgamma, dbeta, dcb, dw_out
     if dpool is not None:
         _lib.call("b200_bn_relu_pool_bwd_apply", _p(z), _p(dy), _p(dpool), _p(mean), _p(rstd), _p(scale), _p(shift),
                   _p(coef[0]), _p(coef[1]), _p(dz), T, B, H, W, C, tstride, _f32(z), _st(), tag=f"C{C} {H}x{W}",
