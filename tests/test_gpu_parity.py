@@ -1024,6 +1024,52 @@ def test_adamw_pack_kernel_matches_update_then_pack(A, B, taps):
     assert torch.equal(w2, w0) and torch.equal(f2, f0)
 
 
+def test_adamw_pack_multi_tensor_launch():
+    """b200_adamw_pack_multi on 20 weights of different shapes at once (two launches of the tile kernel: 16 + 4), one or two
+    packed destinations each, against the multi-tensor update followed by one pack launch per destination: bit-identical."""
+    import unet_convlstm_b200 as pkg
+    from unet_convlstm_b200 import ops, optim
+    g = torch.Generator(device="cuda").manual_seed(77)
+    shapes = [(64, 16, 9), (16, 64, 9), (33, 5, 9), (128, 128, 4), (256, 40, 9), (8, 8, 1), (70, 33, 9), (64, 64, 9),
+              (32, 96, 4), (100, 3, 9), (2, 64, 9), (192, 64, 9), (64, 2, 9), (31, 31, 9), (48, 48, 1), (512, 128, 9),
+              (65, 65, 9), (128, 16, 9), (24, 200, 4), (320, 64, 9)]
+    hyper = (3e-3, 0.9, 0.999, 1e-8, 1e-2)
+    ws = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    grs = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    ms = [0.1 * torch.randn(s, device="cuda", generator=g) for s in shapes]
+    vs = [torch.rand(s, device="cuda", generator=g) for s in shapes]
+    sq = optim.grad_sqnorm(grs)
+
+    def dests(i):
+        A, B, taps = shapes[i]
+        perm = (A // 4, 16) if A % 64 == 0 else (0, 0)
+        f = torch.full((taps, A, B), float("nan"), device="cuda", dtype=torch.bfloat16)
+        geoms = [(A, B, taps, f, 0, 0, 0, A * B, B, *perm)]
+        if i % 3:   # two of three weights also have a data-gradient copy (fp32, transposed, taps flipped)
+            d = torch.full((taps, B, A), float("nan"), device="cuda", dtype=torch.float32)
+            geoms.append((A, B, taps, d, 1, 1, 1, B * A, A, 0, 0))
+        return geoms
+
+    # reference
+    w0, m0, v0 = [w.clone() for w in ws], [m.clone() for m in ms], [v.clone() for v in vs]
+    pkg._lib.call("b200_adamw_multi", len(ws), optim._ptr_array(w0), optim._ptr_array(grs), optim._ptr_array(m0),
+                  optim._ptr_array(v0), optim._numel_array(w0), *hyper, 5, sq, 1.0, ops._st())
+    ref = [dests(i) for i in range(len(ws))]
+    for i, geoms in enumerate(ref):
+        for gm in geoms:
+            ops._pack(w0[i], gm[0], gm[1], gm[2], gm[3], bool(gm[5]), bool(gm[6]), gm[7], gm[8], gm[9], gm[10])
+    # fused, all 20 in one call
+    w1, m1, v1 = [w.clone() for w in ws], [m.clone() for m in ms], [v.clone() for v in vs]
+    got = [dests(i) for i in range(len(ws))]
+    n0 = pkg._lib.CALLS.get("b200_adamw_pack_multi", 0)
+    optim.AdamW._update_and_pack([((w1[i], grs[i], m1[i], v1[i]), got[i]) for i in range(len(ws))], hyper, 5, sq, 1.0)
+    assert pkg._lib.CALLS.get("b200_adamw_pack_multi", 0) == n0 + 1
+    for i in range(len(ws)):
+        assert torch.equal(w1[i], w0[i]) and torch.equal(m1[i], m0[i]) and torch.equal(v1[i], v0[i]), shapes[i]
+        for a, b in zip(got[i], ref[i]):
+            assert torch.equal(a[3], b[3]), shapes[i]   # (no NaN left: every element of every destination was written)
+
+
 @pytest.mark.parametrize("N,K,ks,kpad", [(64, 64, 3, None), (40, 18, 3, 32), (128, 2, 3, 16), (96, 200, 1, None),
                                          (4096, 2048, 3, None)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -1161,11 +1207,11 @@ def test_bn_relu_pool_fused_matches_separate_kernels(mode, shape, training):
             assert np.abs(_np(a) - _np(b)).max() <= 1e-5 * max(np.abs(_np(b)).max(), 1.0)
 
 
-@pytest.mark.parametrize("size", [(16, 16), (20, 12)])
+@pytest.mark.parametrize("size", [(16, 16), (48, 40)])
 def test_model_fused_pool_matches_pool_fork(mode, size):
     """TemporalUNetDualView with the fused BatchNorm/ReLU/max-pool passes against the same model on the separate kernels
     (ops.FUSE_BN_POOL off -> PoolFork): outputs bit-identical, every parameter gradient equal to summation-order noise
-    (20x12 has odd sizes from the third level down: those stages fall back to PoolFork by themselves)."""
+    (48x40 reaches the odd size 6x5 at the fourth level: that stage falls back to PoolFork by itself)."""
     from train.unet import TemporalUNetDualView
     from unet_convlstm_b200 import ops
     H, W = size
@@ -1191,7 +1237,9 @@ def test_model_fused_pool_matches_pool_fork(mode, size):
     finally:
         ops.FUSE_BN_POOL = old
     (y1, g1, s1, c1), (y0, g0, s0, c0) = res
-    assert c1.get("b200_bn_relu_apply_pool", 0) >= 2 and c1.get("b200_bn_relu_pool_bwd_apply", 0) >= 2
+    n_fused = 4 if size == (16, 16) else 3
+    assert c1.get("b200_bn_relu_apply_pool", 0) == n_fused and c1.get("b200_bn_relu_pool_bwd_apply", 0) == n_fused
+    assert c1.get("b200_maxpool2_bwd", 0) == 4 - n_fused
     assert c0.get("b200_bn_relu_apply_pool", 0) == 0 and c0.get("b200_maxpool2_bwd", 0) == 4
     assert torch.equal(y1, y0)
     for k in s0:
@@ -1209,8 +1257,9 @@ def test_model_fused_pool_matches_pool_fork(mode, size):
 @pytest.mark.parametrize("training", [True, False])
 def test_bn_relu_outconv_fused_matches_separate_kernels(mode, shape, training):
     """b200_bn_relu_outconv_fwd / _bwd_reduce / _bwd_apply against b200_bn_relu_apply + b200_outconv_fwd and
-    b200_outconv_bwd + b200_bn_relu_bwd_reduce / _apply.  The fused kernels round the activation and the data gradient
-    of the 1x1 convolution exactly as the separate kernels store them, so only summation orders differ."""
+    b200_outconv_bwd + b200_bn_relu_bwd_reduce / _apply.  fp32 mode: only summation orders differ (1e-5).  bf16 mode: the
+    separate kernels round the activation and the data gradient of the 1x1 convolution to bf16 on their way through HBM,
+    the fused kernels never store either and do not round them: the two agree to that rounding."""
     from unet_convlstm_b200 import ops
     T, B, H, W, C = shape
     dt = ops.act_dtype()
@@ -1229,18 +1278,22 @@ def test_bn_relu_outconv_fused_matches_separate_kernels(mode, shape, training):
     y0, st0 = ops.bn_relu_fwd(z, gamma, beta, rm2, rv2, training, 1e-5, 0.1)
     out0 = ops.outconv_fwd(y0, w, b)
     assert out1.shape == out0.shape and out1.dtype == torch.float32
-    assert rel(_np(out1), _np(out0)) < 1e-5
+    assert rel(_np(out1), _np(out0)) < (1e-5 if mode == "fp32" else 5e-3)
+    if mode == "bf16":   # ... and the fused output is the one closer to exact arithmetic on the same operands
+        exact = (torch.relu(z.double() * st0[2].double().view(-1, 1, 1, 1, C) + st0[3].double().view(-1, 1, 1, 1, C))
+                 * w.double().view(1, 1, 1, 1, C)).sum(-1, keepdim=True) + b.double()
+        assert rel2(_np(out1), _np(exact)) <= rel2(_np(out0), _np(exact)) + 1e-6
     assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
 
     dy0, dw0, db0 = ops.outconv_bwd(y0, w, dout)
     dz0, dg0, dbeta0, dc0 = ops.bn_relu_bwd(z, dy0, st0, training, True)
     dz1, dg1, dbeta1, dc1, dw1 = ops.bn_relu_bwd(z, dout, st1, training, True, outconv_w=w.reshape(-1))
     db1 = ops.colsum(dout.numel(), dout, 1)
-    tol = 1e-5 if mode == "fp32" else 6e-3
+    tol = 1e-5 if mode == "fp32" else 1.2e-2
     assert rel(_np(dz1), _np(dz0)) < tol, rel(_np(dz1), _np(dz0))
-    assert rel2(_np(dz1), _np(dz0)) < (1e-6 if mode == "fp32" else 1e-3)
+    assert rel2(_np(dz1), _np(dz0)) < (1e-6 if mode == "fp32" else 4e-3)
     for a, ref in ((dg1, dg0), (dbeta1, dbeta0), (dc1, dc0), (dw1, dw0.reshape(-1)), (db1, db0)):
-        assert np.abs(_np(a) - _np(ref)).max() <= 1e-5 * max(np.abs(_np(ref)).max(), 1.0)
+        assert np.abs(_np(a) - _np(ref)).max() <= (1e-5 if mode == "fp32" else 3e-3) * max(np.abs(_np(ref)).max(), 1.0)
 
 
 def test_model_fused_outconv_matches_separate(mode):
@@ -1273,9 +1326,17 @@ def test_model_fused_outconv_matches_separate(mode):
     (y1, g1, dx1, c1), (y0, g0, dx0, c0) = res
     assert c1.get("b200_bn_relu_outconv_fwd", 0) == 1 and c1.get("b200_outconv_fwd", 0) == 0
     assert c0.get("b200_bn_relu_outconv_fwd", 0) == 0 and c0.get("b200_outconv_fwd", 0) == 1
-    assert rel(_np(y1), _np(y0)) < 1e-5
+    assert rel(_np(y1), _np(y0)) < (1e-5 if mode == "fp32" else 5e-3)
     g1["x"], g0["x"] = dx1, dx0
     for k in g0:
         a, b = _np(g1[k]), _np(g0[k])
         scale = max(np.abs(b).max(), 1e-6)
         assert np.abs(a - b).max() <= (1e-4 if mode == "fp32" else 3e-2) * scale, (k, np.abs(a - b).max() / scale)
+
+
+def test_image_too_small_for_four_down_stages_raises():
+    """Like the reference (nn.MaxPool2d raises 'Output size is too small'): a 20x12 image is 2x1 at the fourth Down stage."""
+    from train.unet import TemporalUNetDualView
+    m = TemporalUNetDualView(base_ch=8).cuda()
+    with pytest.raises(RuntimeError, match="too small"):
+        m(torch.randn(1, 2, 2, 20, 12, device="cuda"))

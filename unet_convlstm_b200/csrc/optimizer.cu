@@ -74,13 +74,16 @@ __device__ __forceinline__ float clip_coef(const double* sqnorm, float max_norm)
     return c < 1.f ? c : 1.f;
 }
 
+// Every operation is spelled out with rounding intrinsics: left to the compiler, the multiply-adds were contracted
+// differently in the vectorised body, the scalar tail and the tile kernel (adamw_pack_kernel), so the same parameter got
+// last-bit different updates depending on which code path touched it.  One arithmetic, three callers, identical bits.
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamCfg& c, float clip) {
-    g *= clip;
-    p -= c.lr * c.weight_decay * p;
-    m += (g - m) * (1.f - c.beta1);                      // exp_avg.lerp_(grad, 1 - beta1)
-    v = c.beta2 * v + (1.f - c.beta2) * g * g;
-    const float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
-    p -= c.step_size * (m / denom);
+    g = __fmul_rn(g, clip);
+    p = __fmaf_rn(-__fmul_rn(c.lr, c.weight_decay), p, p);                        // p -= lr * wd * p
+    m = __fmaf_rn(__fsub_rn(g, m), __fsub_rn(1.f, c.beta1), m);                   // exp_avg.lerp_(grad, 1 - beta1)
+    v = __fmaf_rn(c.beta2, v, __fmul_rn(__fmul_rn(__fsub_rn(1.f, c.beta2), g), g));
+    const float denom = __fmaf_rn(__fsqrt_rn(v), c.inv_bc2_sqrt, c.eps);
+    p = __fmaf_rn(-c.step_size, __fdiv_rn(m, denom), p);
 }
 
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ MtTable tb, const AdamCfg c,
@@ -136,38 +139,86 @@ __global__ void __launch_bounds__(256) grad_scale_multi_kernel(const __grid_cons
     for (int i = threadIdx.x; i < len; i += 256) g[i] *= clip;
 }
 
-// AdamW of ONE convolution weight [A][B][taps] that also EMITS the GEMM-operand copies of the weight it has just
-// updated ("fused AdamW that also emits the packed bf16 weights"): a block owns a 32 x 32 x taps
-// tile -- 32 runs of 32 * taps contiguous floats of param / grad / exp_avg / exp_avg_sq -- updates it with the
-// arithmetic of adamw_multi_kernel, keeps the new values in shared memory and stores them in up to two packed
-// layouts (pack.cuh; the same stores as pack_weight_kernel).  Replaces one share of the multi-tensor update plus two
-// or three pack launches per weight and step, and the 4 B/param those re-read.
+// AdamW of convolution weights [A][B][taps] that also EMITS the GEMM-operand copies of the weights it has just updated
+// ("fused AdamW that also emits the packed bf16 weights").  A block owns a 32 x 32 x taps tile --
+// 32 runs of 32 * taps contiguous floats of param / grad / exp_avg / exp_avg_sq -- updates it with the arithmetic of
+// adamw_multi_kernel, keeps the new values in shared memory and stores them in up to two packed layouts (pack.cuh; the
+// same stores as pack_weight_kernel).  Multi-tensor: the table of up to AP_MAX weights travels in the kernel parameters
+// and blockIdx.x walks the tiles of all of them, so the 64-parameter first layer and the 75 M-parameter cell weight share
+// one launch (one launch per weight was latency-bound on the small ones: 40 us each for 4 .. 128 blocks, ncu round 2).
+// Replaces the multi-tensor update of these weights plus two or three pack launches per weight and step.
 struct PackDst {
     void* dst;      // nullptr: unused
     int fp32;
     PackGeom g;
 };
 
-__global__ void __launch_bounds__(256) adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                         float* __restrict__ v, int A, int B, int taps, const AdamCfg c,
-                                                         const double* __restrict__ sqnorm, const PackDst d0, const PackDst d1) {
+constexpr int AP_MAX = 16;
+struct ApEntry {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int A, B, taps, tiles_b;
+    PackDst d0, d1;
+};
+struct ApTable {
+    int count;
+    int first_tile[AP_MAX + 1];
+    ApEntry e[AP_MAX];
+};
+static_assert(sizeof(ApTable) + sizeof(AdamCfg) + 16 <= 4096, "the table must fit the classic 4 KB kernel-parameter space");
+
+constexpr int AP_U = 4;  // elements per thread and batch: every load of a batch is issued before the first use
+
+__global__ void __launch_bounds__(256, 4) adamw_pack_kernel(const __grid_constant__ ApTable tb, const AdamCfg c,
+                                                         const double* __restrict__ sqnorm) {
     __shared__ float tile[PK_T][PK_PITCH];
-    const int a0 = blockIdx.y * PK_T, b0 = blockIdx.x * PK_T;
-    const int na = min(PK_T, A - a0), nb = min(PK_T, B - b0);
-    const int run = nb * taps;
+    int t = 0;
+    while (t + 1 < tb.count && static_cast<int>(blockIdx.x) >= tb.first_tile[t + 1]) ++t;
+    const ApEntry& e = tb.e[t];
+    const int tl = blockIdx.x - tb.first_tile[t];
+    const int ty = tl / e.tiles_b;
+    const int a0 = ty * PK_T, b0 = (tl - ty * e.tiles_b) * PK_T;
+    const int na = min(PK_T, e.A - a0), nb = min(PK_T, e.B - b0);
+    const int run = nb * e.taps;              // floats of one row of the tile, contiguous in memory
+    const int run_p = (run + 31) & ~31;       // rows padded to whole warps: a warp never straddles two rows
+    const int total = na * run_p;
     const float clip = clip_coef(sqnorm, c.max_norm);
-    for (int ta = threadIdx.x >> 5; ta < na; ta += 8) {
-        const long long off = (static_cast<long long>(a0 + ta) * B + b0) * taps;
-#pragma unroll 3
-        for (int i = threadIdx.x & 31; i < run; i += 32) {
-            float pp = p[off + i], mm = m[off + i], vv = v[off + i];
-            adamw_one(pp, __ldg(g + off + i), mm, vv, c, clip);
-            p[off + i] = pp, m[off + i] = mm, v[off + i] = vv;
-            tile[ta][i] = pp;
+    float* __restrict__ p = e.p;
+    const float* __restrict__ g = e.g;
+    float* __restrict__ m = e.m;
+    float* __restrict__ v = e.v;
+    for (int base = threadIdx.x; base < total; base += 256 * AP_U) {
+        long long off[AP_U];
+        int ta[AP_U], col[AP_U];
+        float pp[AP_U], gg[AP_U], mm[AP_U], vv[AP_U];
+#pragma unroll
+        for (int u = 0; u < AP_U; ++u) {
+            const int idx = base + u * 256;
+            ta[u] = idx / run_p;
+            col[u] = idx - ta[u] * run_p;
+            const bool ok = idx < total && col[u] < run;
+            if (!ok) ta[u] = -1;
+            off[u] = ok ? (static_cast<long long>(a0 + ta[u]) * e.B + b0) * e.taps + col[u] : 0;
+            if (ok) {
+                pp[u] = p[off[u]];
+                gg[u] = __ldg(g + off[u]);
+                mm[u] = m[off[u]];
+                vv[u] = v[off[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < AP_U; ++u) {
+            if (ta[u] >= 0) {
+                adamw_one(pp[u], gg[u], mm[u], vv[u], c, clip);
+                p[off[u]] = pp[u], m[off[u]] = mm[u], v[off[u]] = vv[u];
+                tile[ta[u]][col[u]] = pp[u];
+            }
         }
     }
     __syncthreads();
-    const PackDst* ds[2] = {&d0, &d1};
+    const PackDst* ds[2] = {&e.d0, &e.d1};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (!ds[k]->dst) continue;
@@ -273,10 +324,76 @@ extern "C" int b200_adamw_multi(int n, void* const* params, const void* const* g
                           });
 }
 
-static bool pack_dst_ok(const void* dst, int A, int taps, long long tap_pitch, long long row_pitch, int perm_ch, int perm_cht) {
+static bool pack_dst_ok(const void* dst, int A, long long tap_pitch, long long row_pitch, long long perm_ch, long long perm_cht) {
     if (!dst) return true;
-    (void)taps;
     return tap_pitch >= 0 && row_pitch > 0 && (perm_ch == 0 || (perm_cht > 0 && perm_ch % perm_cht == 0 && A == 4 * perm_ch));
+}
+
+static AdamCfg adam_cfg(float lr, float beta1, float beta2, float eps, float weight_decay, long long step, float max_norm) {
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+    return AdamCfg{lr, beta1, beta2, eps, weight_decay, static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), max_norm};
+}
+
+// geom: dst_fp32, a_contig, flip, tap_pitch, row_pitch, perm_ch, perm_cht
+static PackDst pack_dst(void* dst, const long long* geom, int A, int B, int taps) {
+    if (!dst) return PackDst{nullptr, 0, PackGeom{A, B, taps, 0, 0, 0, 1, 0, 0}};
+    return PackDst{dst, static_cast<int>(geom[0]),
+                   PackGeom{A, B, taps, geom[1] != 0, geom[2] != 0, geom[3], geom[4], static_cast<int>(geom[5]), static_cast<int>(geom[6])}};
+}
+
+extern "C" int b200_adamw_pack_multi(int n, void* const* params, const void* const* grads, void* const* exp_avg,
+                                     void* const* exp_avg_sq, const long long* dims, float lr, float beta1, float beta2,
+                                     float eps, float weight_decay, long long step, const double* sqnorm, float max_norm,
+                                     void* const* dst0, const long long* geom0, void* const* dst1, const long long* geom1,
+                                     void* stream) {
+    if (n < 0 || (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !dims || !dst0 || !geom0 || !dst1 || !geom1)) ||
+        step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f)) {
+        set_last_error("b200_adamw_pack_multi: bad arguments");
+        return B200_ERR_ARG;
+    }
+    for (int i = 0; i < n; ++i) {
+        const long long A = dims[3 * i], B = dims[3 * i + 1], taps = dims[3 * i + 2];
+        const long long* g0 = geom0 + 7 * i;
+        const long long* g1 = geom1 + 7 * i;
+        if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || A <= 0 || B <= 0 || taps <= 0 || taps > PK_MAX_TAPS ||
+            A > 0x7fffffffLL || B > 0x7fffffffLL || !pack_dst_ok(dst0[i], static_cast<int>(A), g0[3], g0[4], g0[5], g0[6]) ||
+            !pack_dst_ok(dst1[i], static_cast<int>(A), g1[3], g1[4], g1[5], g1[6])) {
+            set_last_error("b200_adamw_pack_multi: weight %d: bad arguments (taps <= %d; the gate interleave needs A = 4*Ch, Ch %% cht = 0)",
+                           i, PK_MAX_TAPS);
+            return B200_ERR_ARG;
+        }
+    }
+    const AdamCfg c = adam_cfg(lr, beta1, beta2, eps, weight_decay, step, max_norm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int i = 0;
+    while (i < n) {
+        ApTable tb;
+        tb.count = 0;
+        tb.first_tile[0] = 0;
+        while (i < n && tb.count < AP_MAX) {
+            const int A = static_cast<int>(dims[3 * i]), B = static_cast<int>(dims[3 * i + 1]), taps = static_cast<int>(dims[3 * i + 2]);
+            const long long tiles_b = (B + PK_T - 1) / PK_T, tiles_a = (A + PK_T - 1) / PK_T;
+            if (tb.first_tile[tb.count] + tiles_a * tiles_b > 0x7fffffffLL) {
+                set_last_error("b200_adamw_pack_multi: too many tiles");
+                return B200_ERR_SHAPE;
+            }
+            ApEntry& e = tb.e[tb.count];
+            e.p = static_cast<float*>(params[i]);
+            e.g = static_cast<const float*>(grads[i]);
+            e.m = static_cast<float*>(exp_avg[i]);
+            e.v = static_cast<float*>(exp_avg_sq[i]);
+            e.A = A; e.B = B; e.taps = taps; e.tiles_b = static_cast<int>(tiles_b);
+            e.d0 = pack_dst(dst0[i], geom0 + 7 * i, A, B, taps);
+            e.d1 = pack_dst(dst1[i], geom1 + 7 * i, A, B, taps);
+            tb.first_tile[tb.count + 1] = tb.first_tile[tb.count] + static_cast<int>(tiles_a * tiles_b);
+            ++tb.count;
+            ++i;
+        }
+        adamw_pack_kernel<<<tb.first_tile[tb.count], 256, 0, st>>>(tb, c, sqnorm);
+        B200_CUDA_CHECK(cudaGetLastError());
+    }
+    return B200_OK;
 }
 
 extern "C" int b200_adamw_pack(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int A, int B, int taps,
@@ -285,25 +402,15 @@ extern "C" int b200_adamw_pack(float* param, const float* grad, float* exp_avg, 
                                long long tap_pitch0, long long row_pitch0, int perm_ch0, int perm_cht0, void* dst1,
                                int dst1_fp32, int a_contig1, int flip1, long long tap_pitch1, long long row_pitch1,
                                int perm_ch1, int perm_cht1, void* stream) {
-    if (!param || !grad || !exp_avg || !exp_avg_sq || A <= 0 || B <= 0 || taps <= 0 || taps > PK_MAX_TAPS || step < 1 ||
-        !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) ||
-        !pack_dst_ok(dst0, A, taps, tap_pitch0, row_pitch0, perm_ch0, perm_cht0) ||
-        !pack_dst_ok(dst1, A, taps, tap_pitch1, row_pitch1, perm_ch1, perm_cht1)) {
-        set_last_error("b200_adamw_pack: bad arguments (taps <= %d; the gate interleave needs A = 4*Ch, Ch %% cht = 0)", PK_MAX_TAPS);
-        return B200_ERR_ARG;
-    }
-    dim3 grid((B + PK_T - 1) / PK_T, (A + PK_T - 1) / PK_T);
-    if (grid.y > 65535) {
-        set_last_error("b200_adamw_pack: A too large");
-        return B200_ERR_SHAPE;
-    }
-    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-    AdamCfg c{lr, beta1, beta2, eps, weight_decay, static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), max_norm};
-    PackDst d0{dst0, dst0_fp32, PackGeom{A, B, taps, a_contig0 != 0, flip0 != 0, tap_pitch0, row_pitch0, perm_ch0, perm_cht0}};
-    PackDst d1{dst1, dst1_fp32, PackGeom{A, B, taps, a_contig1 != 0, flip1 != 0, tap_pitch1, row_pitch1, perm_ch1, perm_cht1}};
-    adamw_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, A, B, taps, c,
-                                                                            sqnorm, d0, d1);
-    B200_CUDA_CHECK(cudaGetLastError());
-    return B200_OK;
+    void* ps[1] = {param};
+    const void* gs[1] = {grad};
+    void* ms[1] = {exp_avg};
+    void* vs[1] = {exp_avg_sq};
+    void* d0[1] = {dst0};
+    void* d1[1] = {dst1};
+    const long long dims[3] = {A, B, taps};
+    const long long g0[7] = {dst0_fp32, a_contig0, flip0, tap_pitch0, row_pitch0, perm_ch0, perm_cht0};
+    const long long g1[7] = {dst1_fp32, a_contig1, flip1, tap_pitch1, row_pitch1, perm_ch1, perm_cht1};
+    return b200_adamw_pack_multi(1, ps, gs, ms, vs, dims, lr, beta1, beta2, eps, weight_decay, step, sqnorm, max_norm, d0, g0, d1,
+                                 g1, stream);
 }

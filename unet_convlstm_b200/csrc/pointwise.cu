@@ -1157,8 +1157,9 @@ int launch_bn_relu_pool_bwd_apply(const void* x, const void* dy, const void* dp,
 // product dout[p] * w[c], so the BatchNorm-backward passes form it on the fly instead of reading a stored tensor, and
 // the weight gradient dw[c] = sum_p dout[p] * y[p][c] rides along in the reduction pass with y recomputed.  Separately
 // that is apply (r + w) + outconv (r) forward and outconv wgrad (r) + dgrad (w) + BatchNorm sums (2r) + apply (2r + w)
-// backward = 10 passes over the largest activation tensor of the network; fused it is 1 + 1 + 2.  Roundings follow the
-// separate kernels (y and the data gradient as they would have been STORED in T), the summation orders differ.
+// backward = 10 passes over the largest activation tensor of the network; fused it is 1 + 1 + 2.  The activation and the
+// data gradient of the 1x1 convolution are never stored, so they are not rounded to T either (the separate kernels round
+// both to bf16 on the way through HBM): the fused results sit closer to exact arithmetic by those two roundings.
 // A pixel's C / V channel vectors sit in C / V consecutive lanes (a power of two <= 32).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int V>
@@ -1201,7 +1202,7 @@ __global__ void __launch_bounds__(256) bn_relu_outconv_fwd_kernel(const T* __res
                 float f[V];
                 unpack_raw<T, V>(rx[u], f);
 #pragma unroll
-                for (int j = 0; j < V; ++j) acc = fmaf(as_stored<T>(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f)), wv[j], acc);
+                for (int j = 0; j < V; ++j) acc = fmaf(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f), wv[j], acc);
             }
             for (int s = g.cvb >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
             if (p < p_end && cv == 0) out[base + p] = acc + bias;
@@ -1256,10 +1257,12 @@ int launch_bn_relu_outconv_fwd(const void* x, const float* scale, const float* s
     return B200_OK;
 }
 
-// sum_g[t][c] = sum_p g, sum_gx[t][c] = sum_p g * xhat (as BnBwdReduceOp) with g = stored(dout[p] * w[c]) * [relu active],
-// and dw[c] += sum_p dout[p] * stored(y[p][c]) over ALL t.  Same block / thread layout as colreduce_kernel.
+// sum_g[t][c] = sum_p g, sum_gx[t][c] = sum_p g * xhat (as BnBwdReduceOp) with g = dout[p] * w[c] * [relu active], and
+// dw[c] += sum_p dout[p] * y[p][c] over ALL t.  Same block / thread layout as colreduce_kernel.  One 16-byte vector and
+// one scalar per row: eight rows in flight per thread at two blocks per SM (ncu of the first version, four rows at
+// three blocks: 2.7 TB/s with the warps waiting on their loads).
 template <typename T, int V, typename Acc>
-__global__ void __launch_bounds__(256, (std::is_same<T, float>::value ? 2 : 3))
+__global__ void __launch_bounds__(256, 2)
 bn_relu_outconv_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ dout, const float* __restrict__ w,
                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                   const float* __restrict__ scale, const float* __restrict__ shift, const ReduceGeom g,
@@ -1291,13 +1294,13 @@ bn_relu_outconv_bwd_reduce_kernel(const T* __restrict__ x, const float* __restri
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const float yv = fmaf(fx[j], sc[j], sh[j]);
-            const float gq = yv > 0.f ? as_stored<T>(d * wv[j]) : 0.f;
+            const float gq = yv > 0.f ? d * wv[j] : 0.f;
             a0[j] += Acc(gq);
             a1[j] += Acc(gq) * Acc(fx[j]);
-            a2[j] += Acc(d) * Acc(as_stored<T>(fmaxf(yv, 0.f)));
+            a2[j] += Acc(d) * Acc(fmaxf(yv, 0.f));
         }
     };
-    constexpr int U = 4;
+    constexpr int U = 8;
     const long long step = g.rows_per_iter;
     long long p = p_begin + r;
     for (; p + (U - 1) * step < p_end; p += U * step) {
@@ -1364,9 +1367,9 @@ int launch_bn_relu_outconv_bwd_reduce(const void* x, const float* dout, const fl
         g.T = T_; g.P = P; g.C = C;
         g.cvb = C / V;
         g.rows_per_iter = 256 / g.cvb;
-        // two full waves at three resident blocks per SM, at least 4 iterations per thread (see launch_colreduce)
-        long long want_x = (6LL * num_sms()) / T_;
-        long long max_x = (P + 4LL * g.rows_per_iter - 1) / (4LL * g.rows_per_iter);
+        // two full waves at two resident blocks per SM, at least 8 iterations per thread (see launch_colreduce)
+        long long want_x = (4LL * num_sms()) / T_;
+        long long max_x = (P + 8LL * g.rows_per_iter - 1) / (8LL * g.rows_per_iter);
         if (want_x > max_x) want_x = max_x;
         if (want_x < 1) want_x = 1;
         g.rows_per_block = (P + want_x - 1) / want_x;
@@ -1421,7 +1424,7 @@ bn_relu_outconv_bwd_apply_kernel(const T* __restrict__ x, const float* __restric
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const float yv = fmaf(fx[j], sc[j], sh[j]);
-            const float gq = yv > 0.f ? as_stored<T>(d * wv[j]) : 0.f;
+            const float gq = yv > 0.f ? d * wv[j] : 0.f;
             fd[j] = fmaf(sc[j], gq, fmaf(ka[j], fx[j], kb[j]));
         }
         stv<T, V>(dx + off, fd);

@@ -470,6 +470,10 @@ def bn_relu_bwd(z, dy, stats, training, want_dbias=False, dpool=None, outconv_w=
 def maxpool2_fwd(x):
     _chk(x, "x")
     T, B, H, W, C = x.shape
+    if H < 2 or W < 2:
+        # nn.MaxPool2d(2) of the reference raises here too (an image smaller than 16 pixels on a side reaches the fourth Down
+        # stage below 2x2); without this the empty tensor would travel on into the convolutions
+        raise RuntimeError(f"max_pool2d(2): input {H}x{W} is too small (output size would be {H // 2}x{W // 2})")
     y = torch.empty((T, B, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
     _lib.call("b200_maxpool2_fwd", _p(x), _p(y), T * B, H, W, C, _f32(x), _st())
     return y

@@ -35,6 +35,7 @@ def _numel_array(tensors):
 
 
 MT_MAX = 48  # tensors per kernel launch (csrc/optimizer.cu): calls are split so that one call = one launch
+AP_MAX = 16  # weights per launch of the update-and-pack tile kernel
 
 
 def _chunks(seq):
@@ -136,15 +137,17 @@ class AdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             hyper = (float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
             for t, its in by_step.items():
-                # weights with packed copies in a WeightCache: one launch each that updates AND re-packs
-                rest = []
+                # weights with packed copies in a WeightCache: tile kernel that updates AND re-packs, 16 weights per launch
+                rest, packed = [], []
                 for it in its:
                     geoms = packs.get(it[0].data_ptr())
                     if geoms:
                         _check(it[2:], "AdamW.step (moments)")
-                        self._update_and_pack(it, geoms, hyper, t, sq, clip_max_norm)
+                        packed.append((it, geoms))
                     else:
                         rest.append(it)
+                for i in range(0, len(packed), AP_MAX):
+                    self._update_and_pack(packed[i:i + AP_MAX], hyper, t, sq, clip_max_norm)
                 for items in _chunks(rest):
                     P, G, M, V = ([it[k] for it in items] for k in range(4))
                     _check(M, "AdamW.step (exp_avg)"), _check(V, "AdamW.step (exp_avg_sq)")
@@ -157,16 +160,21 @@ class AdamW(torch.optim.Optimizer):
         return loss
 
     @staticmethod
-    def _update_and_pack(item, geoms, hyper, t, sq, clip_max_norm):
-        """b200_adamw_pack on one weight: the update plus its first two packed copies; further copies (none in this
-        package's models) through b200_pack_weight."""
-        p, g, m, v = item
-        A, B, taps = geoms[0][:3]
+    def _update_and_pack(items, hyper, t, sq, clip_max_norm):
+        """b200_adamw_pack_multi on up to AP_MAX weights: the update plus the first two packed copies of each; further
+        copies (none in this package's models) through b200_pack_weight."""
+        n = len(items)
+        P, G, M, V = ([it[k] for it, _ in items] for k in range(4))
+        LL = ctypes.c_longlong
+        dims = (LL * (3 * n))(*[x for _, geoms in items for x in geoms[0][:3]])
         none = (None, 0, 0, 0, 0, 1, 0, 0)
-        d0 = geoms[0][3:]
-        d1 = geoms[1][3:] if len(geoms) > 1 else none
-        _lib.call("b200_adamw_pack", _p(p), _p(g), _p(m), _p(v), A, B, taps, *hyper, t, _p(sq), float(clip_max_norm or 0.0),
-                  *d0, *d1, _st())
-        bump_version(p, m, v)
-        for geom in geoms[2:]:
-            _lib.call("b200_pack_weight", _p(p.detach()), *geom[:3], _p(geom[3]), *geom[4:], _st())
+        d0 = [geoms[0][3:] for _, geoms in items]
+        d1 = [geoms[1][3:] if len(geoms) > 1 else none for _, geoms in items]
+        ptrs = lambda ds: (ctypes.c_void_p * n)(*[None if d[0] is None else d[0].data_ptr() for d in ds])
+        geom = lambda ds: (LL * (7 * n))(*[int(x) for d in ds for x in d[1:]])
+        _lib.call("b200_adamw_pack_multi", n, _ptr_array(P), _ptr_array(G), _ptr_array(M), _ptr_array(V), dims, *hyper, t,
+                  _p(sq), float(clip_max_norm or 0.0), ptrs(d0), geom(d0), ptrs(d1), geom(d1), _st())
+        bump_version(*P, *M, *V)
+        for (p, _, _, _), geoms in items:
+            for g in geoms[2:]:
+                _lib.call("b200_pack_weight", _p(p.detach()), *g[:3], _p(g[3]), *g[4:], _st())
