@@ -977,7 +977,7 @@ def test_packed_weights_follow_the_optimizer(which):
     assert rel(_np(xa.grad), _np(xb.grad)) < 1e-4, rel(_np(xa.grad), _np(xb.grad))
     if which == "b200" and optim.ADAMW_PACK:
         # the update kernel emitted the packed copies itself: no weight was re-packed by these two forward/backward passes
-        assert pkg._lib.CALLS.get("b200_adamw_pack", 0) > 0
+        assert pkg._lib.CALLS.get("b200_adamw_pack_multi", 0) > 0
         n0 = pkg._lib.CALLS.get("b200_pack_weight", 0)
         opt.zero_grad(set_to_none=True)
         (torch.stack(m(x)[0], dim=1) * dy).sum().backward()
@@ -1293,7 +1293,9 @@ def test_bn_relu_outconv_fused_matches_separate_kernels(mode, shape, training):
     assert rel(_np(dz1), _np(dz0)) < tol, rel(_np(dz1), _np(dz0))
     assert rel2(_np(dz1), _np(dz0)) < (1e-6 if mode == "fp32" else 4e-3)
     for a, ref in ((dg1, dg0), (dbeta1, dbeta0), (dc1, dc0), (dw1, dw0.reshape(-1)), (db1, db0)):
-        assert np.abs(_np(a) - _np(ref)).max() <= (1e-5 if mode == "fp32" else 3e-3) * max(np.abs(_np(ref)).max(), 1.0)
+        # (bf16: the separate path's gradient is rounded to bf16 element by element, 4e-3 each; over the 18 .. 1152 pixels of
+        # these problems that does not average out below ~1e-2)
+        assert np.abs(_np(a) - _np(ref)).max() <= (1e-5 if mode == "fp32" else 1.5e-2) * max(np.abs(_np(ref)).max(), 1.0)
 
 
 def test_model_fused_outconv_matches_separate(mode):
