@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256, 4) adamw_pack_kernel(const __grid_constan
     const int run = nb * e.taps;              // floats of one row of the tile, contiguous in memory
     const int run_p = (run + 31) & ~31;       // rows padded to whole warps: a warp never straddles two rows
     const int total = na * run_p;
+    const unsigned inv_run_p = static_cast<unsigned>((0x100000000ULL + run_p - 1) / run_p);  // idx / run_p = umulhi(idx, inv): exact for idx < 2^32 / run_p
     const float clip = clip_coef(sqnorm, c.max_norm);
     float* __restrict__ p = e.p;
     const float* __restrict__ g = e.g;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256, 4) adamw_pack_kernel(const __grid_constan
 #pragma unroll
         for (int u = 0; u < AP_U; ++u) {
             const int idx = base + u * 256;
-            ta[u] = idx / run_p;
+            ta[u] = static_cast<int>(__umulhi(static_cast<unsigned>(idx), inv_run_p));
             col[u] = idx - ta[u] * run_p;
             const bool ok = idx < total && col[u] < run;
             if (!ok) ta[u] = -1;
