@@ -41,6 +41,7 @@ def dry(monkeypatch):
     monkeypatch.setattr(ops, "copy_", lambda dst, src, accumulate=False: (dst.add_(src) if accumulate else dst.copy_(src)))
     monkeypatch.setattr(ops, "_pack_ok", lambda w, taps: w.dtype == torch.float32 and taps <= 9)
     monkeypatch.setattr(U, "_require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(ops, "WGRAD_STREAM", False)   # (another test of the session may have opted in; streams need a device)
     if hasattr(loss, "_st"):
         monkeypatch.setattr(loss, "_st", lambda: 0)
     old = ops.get_precision()
