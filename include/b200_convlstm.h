@@ -295,8 +295,8 @@ int b200_grad_clip_multi(int n, void* const* grads, const long long* numel, cons
 int b200_adamw_multi(int n, void* const* params, const void* const* grads, void* const* exp_avg,
                      void* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
                      float weight_decay, long long step, const double* sqnorm, float max_norm, void* stream);
-/* AdamW of convolution weights [A][B][taps] fp32 (OIHW: A = Cout, B = Cin; IOHW for ConvTranspose2d) that also emits the
- * GEMM-operand copies of the UPDATED weights -- SURVEY section 8 f1, "fused AdamW that also emits the packed bf16
+/* AdamW (main.py:275) of convolution weights [A][B][taps] fp32 (OIHW: A = Cout, B = Cin; IOHW for ConvTranspose2d) that also
+ * emits the GEMM-operand copies of the UPDATED weights -- SURVEY section 8 f1, "fused AdamW that also emits the packed bf16
  * weights": same arithmetic as b200_adamw_multi (bit-identical), then up to two destinations per weight in the layouts
  * of b200_pack_weight.  b200_adamw_pack_multi: n weights in one launch per 16; host tables like b200_adamw_multi,
  * dims = [n][3] {A, B, taps}, dst0 / dst1 = [n] device pointers (NULL = unused), geom0 / geom1 = [n][7]
