@@ -436,3 +436,24 @@ def test_run_reference_launcher_runs_overfit_check_unchanged_cpu(tmp_path):
     res = json.loads(out.read_text())
     assert list(res["curve"]) == ["0"] and 0 < res["curve"]["0"] < 10
     assert "Starting Overfit Test (custom)" in r.stdout
+
+
+def test_maxpool_tie_breaking_matches_aten():
+    """The max-pool backward of this repository (maxpool2_bwd_kernel and the fused BatchNorm / ReLU / pool backward) and the
+    numpy oracle route the gradient of a window to its FIRST maximum in scan order (0,0),(0,1),(1,0),(1,1).  After a ReLU
+    whole windows are exactly zero, so ties are the common case, not a corner: pin the rule against ATen
+    (nn.MaxPool2d(2), reference unet.py:81) on windows with every tie pattern, and the oracle against it."""
+    import itertools
+    import numpy as np
+    import torch
+    from oracle import unet_oracle as O
+    pats = list(itertools.product([0.0, 1.0], repeat=4))            # 16 tie patterns of a 2x2 window
+    x = torch.tensor(pats, dtype=torch.float64).reshape(1, 16, 2, 2).clone().requires_grad_(True)
+    torch.nn.functional.max_pool2d(x, 2).sum().backward()
+    got = x.grad.reshape(16, 4)
+    for p, g in zip(pats, got):
+        first = p.index(max(p))
+        assert g.tolist() == [1.0 if k == first else 0.0 for k in range(4)], (p, g)
+    y, cache = O.maxpool2_fwd(x.detach().numpy())
+    dx = O.maxpool2_bwd(cache, np.ones_like(y))
+    assert np.array_equal(dx.reshape(16, 4), got.numpy())
